@@ -1,0 +1,144 @@
+/*
+ * libmimamo_b200.so -- C ABI of the B200-native MIMAMO-Net per-window inference hot path.
+ *
+ * The reference (wtomin/MIMAMO-Net) is 100 % Python over PyTorch library calls and has no
+ * FFI of its own; the drop-in boundary is its `api/` class surface.
+ * The Python classes under `mimamo-net_b200/api/` keep that surface and call the entry points
+ * below through ctypes.  Each entry point names the reference code it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every call returns 0 on success, <0 on error; mimamo_last_error() returns a thread-local
+ *     message which the Python layer re-raises as the matching exception type
+ *     (MIMAMO_E_VALUE -> ValueError, MIMAMO_E_RUNTIME/CUDA -> RuntimeError);
+ *   - all data pointers are DEVICE pointers unless the name ends in `_host`; the caller owns
+ *     every buffer (outputs and workspaces are never allocated here); plans / nets own only
+ *     their immutable tables and weights;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and the calls
+ *     never synchronise the device;
+ *   - plain pointers and sizes only: no torch / C++ types cross this boundary.
+ */
+#ifndef MIMAMO_B200_H_
+#define MIMAMO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMAMO_OK          0
+#define MIMAMO_E_VALUE    -1   /* bad argument (ValueError)                     */
+#define MIMAMO_E_RUNTIME  -2   /* unsupported configuration (RuntimeError)      */
+#define MIMAMO_E_CUDA     -3   /* CUDA runtime / driver failure (RuntimeError)  */
+
+#define MIMAMO_MAX_LEVELS  8
+
+int         mimamo_abi_version(void);
+const char* mimamo_last_error(void);
+/* number of kernels this library has launched on the calling process so far (bench.py's
+ * `gpu_launches`). */
+uint64_t    mimamo_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * P0 + P1: complex steerable pyramid of mirror-extended frames.
+ * Replaces symmetric_extension_batch (api/utils/phase_utils.py:116-129),
+ * SCFpyr_PyTorch.build/_build_levels (api/steerable/SCFpyr_PyTorch.py:70-208) and the
+ * stack/permute/crop in Phase_Difference_Extractor.build_pyramid
+ * (api/phase_difference_extractor.py:38-87).
+ * The data-independent tables are built on the host exactly like the reference builds its
+ * masks (np.interp; mimamo-net_b200/api/steerable/plan_tables.py) and uploaded once.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mimamo_pyr_plan mimamo_pyr_plan;
+
+typedef struct {
+  int32_t c;                 /* kept crop: outputs y,x in [0,c)                              */
+  int32_t h;                 /* folded frequency count                                        */
+  int32_t hp, cp;            /* h, c padded to multiples of 4 (leading dimensions)            */
+  const float*   trig_host;  /* [2][hp][cp]  cos/sin(pi k/S + 2 pi k y/s)                     */
+  const float*   masks_host; /* [nbands][2 ch][2 half][hp][hp], transposed ([l][k])           */
+  const int32_t* inner_sel_host; /* [2 ch][2 half]: 0 = cos table, 1 = sin table              */
+} mimamo_pyr_level_desc;
+
+int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t nbands,
+                           const float* dct_t_host /* [Hp][Kp] */,
+                           int32_t n_levels, const mimamo_pyr_level_desc* levels,
+                           mimamo_pyr_plan** plan_out);
+void mimamo_pyr_plan_destroy(mimamo_pyr_plan* plan);
+
+/* frames f32[n_windows*T, H, H]  ->  coeff_out[level] f32[n_windows, nbands, T, c, c, 2]
+ * (the layout Phase_Difference_Extractor.build_pyramid returns). */
+int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames,
+                     int64_t n_windows, int32_t T, float* const* coeff_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P2: phase tail.  Replaces Phase_Difference_Extractor.extract
+ * (api/phase_difference_extractor.py:93-134) with torch_unwrap / torch_diff /
+ * amplitude_based_gaussian_blur / gaussian_kernel (api/utils/phase_utils.py:5-40,78-90,108-115).
+ * coeff f32[n_maps, T, rows, cols, 2] -> out f32[n_maps, T-1, rows, cols], n_maps = bs*nbands.
+ * ---------------------------------------------------------------------------------------- */
+int mimamo_phase_extract_workspace_bytes(int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
+                                         size_t* bytes_out);
+int mimamo_phase_extract(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * P3: frames -> phase-difference maps without materialising coefficients in the caller.
+ * Replaces Tester.phase_diff_output (api/tester.py:122-139).
+ * frames f32[n_windows*T,H,H] -> out[level] f32[n_windows, nbands*(T-1), c, c].
+ * ---------------------------------------------------------------------------------------- */
+int mimamo_pyr_phase_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T,
+                                     size_t* bytes_out);
+int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
+                     float* const* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution network engine (rows R and H of SURVEY.md section 8(a)).
+ * A net is a flat table of named host tensors (the reference-keyed state_dict) folded once
+ * into bf16 NHWC implicit-GEMM weights + fp32 scale/shift (eval-mode BatchNorm).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const char*    name;       /* state_dict key                                               */
+  const float*   data_host;  /* fp32, contiguous, torch layout                               */
+  int32_t        ndim;
+  int64_t        shape[4];
+} mimamo_tensor_desc;
+
+/* R: ResNet50 pool5.  Replaces Resnet50_Extractor.get_vec (api/resnet50_extractor.py:74-83)
+ * over the third-party resnet50_ferplus_dag module (api/utils/model_utils.py:65-79).
+ * x f32[B,3,224,224] (0-255 scale minus mean, NCHW as the reference feeds it)
+ * -> out f32[B,2048] = relu(pool5_7x7_s1). */
+typedef struct mimamo_resnet50 mimamo_resnet50;
+int  mimamo_resnet50_create(const mimamo_tensor_desc* tensors, int32_t n_tensors,
+                            mimamo_resnet50** net_out);
+void mimamo_resnet50_destroy(mimamo_resnet50* net);
+int  mimamo_resnet50_workspace_bytes(const mimamo_resnet50* net, int32_t batch, size_t* bytes_out);
+int  mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x, int32_t batch, float* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* H: two-stream head.  Replaces Two_Stream_RNN.forward (api/mimamo_net.py:129-143; MLP :22-26,
+ * PhaseNet :79-95; GRU built without batch_first at :119, so it recurs over dim 0 = bs).
+ * phase_0 f32[bs,nf,24,48,48], phase_1 f32[bs,nf,24,24,24], rgb f32[bs,nf,2048]
+ * -> out f32[bs,nf,2] = [valence, arousal]. */
+typedef struct mimamo_head mimamo_head;
+int  mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_phase,
+                        mimamo_head** head_out);
+void mimamo_head_destroy(mimamo_head* head);
+int  mimamo_head_workspace_bytes(const mimamo_head* head, int32_t bs, int32_t nf, size_t* bytes_out);
+int  mimamo_head_forward(const mimamo_head* head, const float* phase_0, const float* phase_1,
+                         const float* rgb, int32_t bs, int32_t nf, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook: one conv layer through the tcgen05 implicit-GEMM engine.
+ * x bf16 NHWC [B,H,W,Cin] (Cin multiple of 8), w f32 [Cout,Cin,k,k] (torch layout),
+ * scale/shift f32[Cout], optional residual bf16 NHWC of the output shape, out bf16 NHWC. */
+int mimamo_conv_bf16(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin,
+                     const float* w_host, const float* scale_host, const float* shift_host,
+                     int32_t Cout, int32_t ksize, int32_t stride, int32_t pad, int32_t relu,
+                     const void* residual, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMAMO_B200_H_ */

@@ -1,0 +1,99 @@
+"""Native net handles: a reference-keyed state_dict -> mimamo_resnet50 / mimamo_head (C ABI)."""
+import ctypes
+
+import numpy as np
+import torch
+
+import _native
+
+
+def _tensor_table(state_dict):
+    """(ctypes array of mimamo_tensor_desc, keep-alive list) for every floating tensor."""
+    items = [(k, v) for k, v in state_dict.items() if torch.is_tensor(v) and v.is_floating_point()]
+    table = (_native.TensorDesc * len(items))()
+    keep = []
+    for d, (k, v) in zip(table, items):
+        arr = np.ascontiguousarray(v.detach().to('cpu', torch.float32).numpy())
+        name = k.encode()
+        keep += [arr, name]
+        d.name = name
+        d.data_host = _native.f32_host_ptr(arr)
+        d.ndim = arr.ndim
+        if arr.ndim > 4:
+            raise ValueError('tensor %s has more than 4 dims' % k)
+        for i, s in enumerate(arr.shape):
+            d.shape[i] = s
+    return table, len(items), keep
+
+
+class _Handle(object):
+    _destroy = None
+
+    def __init__(self):
+        self.handle = _native.vp()
+        self._ws = None
+
+    def workspace(self, nbytes, device):
+        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != device:
+            self._ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def __del__(self):
+        try:
+            if self.handle:
+                getattr(_native.lib(), self._destroy)(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class NativeResNet50(_Handle):
+    _destroy = 'mimamo_resnet50_destroy'
+
+    def __init__(self, state_dict):
+        super().__init__()
+        _native.require_cuda('Resnet50_Extractor')
+        table, n, keep = _tensor_table(state_dict)
+        _native.check(_native.lib().mimamo_resnet50_create(table, n, ctypes.byref(self.handle)))
+
+    def pool5(self, image):
+        """image (bs,3,224,224) float32 CUDA, 0-255 scale minus mean -> (bs,2048) float32 CUDA."""
+        assert image.is_cuda and image.dtype == torch.float32 and tuple(image.shape[1:]) == (3, 224, 224), \
+            'expected a float32 CUDA batch of shape (bs,3,224,224)'
+        image = image.contiguous()
+        bs = image.shape[0]
+        out = torch.empty((bs, 2048), dtype=torch.float32, device=image.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_resnet50_workspace_bytes(self.handle, bs, ctypes.byref(need)))
+        ws = self.workspace(need.value, image.device)
+        _native.check(lib.mimamo_resnet50_pool5(self.handle, _native.dptr(image), bs, _native.dptr(out), _native.dptr(ws),
+                                                ws.numel(), _native.stream_ptr(image.device)))
+        return out
+
+
+class NativeHead(_Handle):
+    _destroy = 'mimamo_head_destroy'
+
+    def __init__(self, state_dict, num_phase=12):
+        super().__init__()
+        _native.require_cuda('Two_Stream_RNN')
+        table, n, keep = _tensor_table(state_dict)
+        _native.check(_native.lib().mimamo_head_create(table, n, num_phase, ctypes.byref(self.handle)))
+
+    def forward(self, phase_0, phase_1, rgb):
+        bs, nf = rgb.shape[0], rgb.shape[1]
+        for t in (phase_0, phase_1, rgb):
+            assert t.is_cuda and t.dtype == torch.float32, 'head inputs must be float32 CUDA tensors'
+        assert tuple(phase_0.shape) == (bs, nf, 24, 48, 48) and tuple(phase_1.shape) == (bs, nf, 24, 24, 24) \
+            and rgb.shape[2] == 2048, 'unexpected head input shapes'
+        phase_0, phase_1, rgb = phase_0.contiguous(), phase_1.contiguous(), rgb.contiguous()
+        out = torch.empty((bs, nf, 2), dtype=torch.float32, device=rgb.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_head_workspace_bytes(self.handle, bs, nf, ctypes.byref(need)))
+        ws = self.workspace(need.value, rgb.device)
+        _native.check(lib.mimamo_head_forward(self.handle, _native.dptr(phase_0), _native.dptr(phase_1), _native.dptr(rgb),
+                                              bs, nf, _native.dptr(out), _native.dptr(ws), ws.numel(),
+                                              _native.stream_ptr(rgb.device)))
+        return out

@@ -1,0 +1,144 @@
+"""Drop-in for api/tester.py: the end-to-end orchestrator, plus a device-resident clip path.
+
+`Tester.test` / `test_on_dataloader` / `phase_diff_output` keep the reference's signatures and
+return types (api/tester.py:53-139).  `infer_clips` is the B200 fast path used by bench.py and
+the multi-GPU driver: gray windows + RGB frames go in, valence/arousal comes out, and the ResNet
+features never leave the device (no .npy round trip).
+"""
+import os
+
+import numpy as np
+import torch
+
+from phase_difference_extractor import Phase_Difference_Extractor
+from mimamo_net import Two_Stream_RNN
+from steerable.utils import get_device
+
+device = get_device()
+
+
+class Tester(object):
+    def __init__(self,
+                 model_path,
+                 batch_size,
+                 workers=0,
+                 save_size=112, nomask=True, grey=False, quiet=True,
+                 tracked_vid=False, noface_save=False,
+                 OpenFace_exe='OpenFace/build/bin/FeatureExtraction',
+                 benchmark_dir='pytorch-benchmarks', model_name='resnet50_ferplus_dag',
+                 feature_layer='pool5_7x7_s1',
+                 num_phase=12, phase_size=48,
+                 length=64, stride=64,
+                 height=4, nbands=2, scale_factor=2,
+                 extract_level=[1, 2],
+                 resnet_model=None, head_state_dict=None):
+        '''Reference arguments (:15-33) plus two optional in-memory weight sources:
+        resnet_model (nn.Module / state_dict) and head_state_dict.  When both are given no files,
+        OpenFace binary or third-party checkpoint are needed (synthetic runs).'''
+        from resnet50_extractor import Resnet50_Extractor
+        self.batch_size = batch_size
+        self.workers = workers
+        self.num_phase = num_phase
+        self.phase_size = phase_size
+        self.length = length
+        self.stride = stride
+        synthetic = resnet_model is not None and head_state_dict is not None
+        if synthetic:
+            self.video_processor = None
+        else:
+            from video_processor import Video_Processor
+            self.video_processor = Video_Processor(save_size, nomask, grey, quiet, tracked_vid, noface_save, OpenFace_exe)
+        self.resnet50_extractor = Resnet50_Extractor(benchmark_dir, model_name, feature_layer, model=resnet_model)
+        self.phase_difference_extractor = Phase_Difference_Extractor(height, nbands, scale_factor, extract_level, not quiet)
+        self.model = Two_Stream_RNN(num_phase=num_phase)
+        if head_state_dict is None:
+            assert os.path.exists(model_path)
+            checkpoint = torch.load(model_path, map_location='cpu')
+            self.model.load_state_dict(checkpoint['state_dict'])
+            print("load checkpoint from {}, epoch:{}".format(model_path, checkpoint['epoch']))
+        else:
+            self.model.load_state_dict(head_state_dict)
+        self.model.to(device)
+        self.model.eval()
+        self.label_name = ['valence', 'arousal']
+
+    # ------------------------------------------------------------------ reference surface
+    def test(self, input_video):
+        from sampler.snippet_sampler import Snippet_Sampler
+        if self.video_processor is None:
+            raise RuntimeError('this Tester was built from in-memory weights without OpenFace; use infer_clips')
+        video_name = os.path.basename(input_video).split('.')[0]
+        opface_output_dir = os.path.join(os.path.dirname(input_video), video_name + "_opface")
+        self.video_processor.process(input_video, opface_output_dir)
+        feature_dir = os.path.join(os.path.dirname(input_video), video_name + "_pool5")
+        self.resnet50_extractor.run(opface_output_dir, feature_dir, video_name=video_name)
+        dataset = Snippet_Sampler(video_name, opface_output_dir, feature_dir, annot_dir=None,
+                                  label_name='valence_arousal', test_mode=True, num_phase=self.num_phase,
+                                  phase_size=self.phase_size, length=self.length, stride=self.stride)
+        data_loader = torch.utils.data.DataLoader(dataset, batch_size=self.batch_size, num_workers=self.workers,
+                                                  pin_memory=True)
+        return self.test_on_dataloader(data_loader, self.model)
+
+    def test_on_dataloader(self, dataloader, model, train_mean=None, train_std=None):
+        import pandas as pd
+        model.eval()
+        names, preds, ranges = [], [], []
+        for phase_f, rgb_f, label, rng, name in dataloader:
+            with torch.no_grad():
+                phase_f = phase_f.float().to(device, non_blocking=True)
+                rgb_f = torch.as_tensor(rgb_f).float().to(device, non_blocking=True)
+                phase_0, phase_1 = self.phase_diff_output(phase_f, self.phase_difference_extractor)
+                output = model([phase_0, phase_1], rgb_f)
+            names.append(np.asarray(name))
+            ranges.append(np.asarray(rng))
+            preds.append(output.cpu().numpy())
+        names = np.concatenate(names, axis=0)
+        preds = np.concatenate(preds, axis=0)
+        ranges = np.concatenate(ranges, axis=0)
+        if train_mean is not None and train_std is not None:
+            # the reference calls an undefined `correct` here (api/tester.py:101); rescale each label
+            for i in range(preds.shape[-1]):
+                p = preds[..., i]
+                preds[..., i] = (p - p.mean()) / (p.std() + 1e-12) * train_std[i] + train_mean[i]
+        return {video: pd.DataFrame(data=arr, columns=self.label_name)
+                for video, arr in stitch_predictions(names, ranges, preds).items()}
+
+    def phase_diff_output(self, phase_batch, steerable_pyramid):
+        """(bs, frames, T, W, H) gray windows -> [phase_0 (bs,frames,nb*(T-1),W,H), phase_1 (.., W/2, H/2)]."""
+        sp = steerable_pyramid
+        bs, num_frames, num_phases, W, H = phase_batch.size()
+        diffs = sp.phase_difference(phase_batch.view(bs * num_frames, num_phases, W, H))
+        assert isinstance(diffs, list)
+        outs = [d.view(bs, num_frames, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+        return outs[0], outs[1]
+
+    # ------------------------------------------------------------------ B200 clip path
+    def infer_clips(self, gray_windows, rgb_frames):
+        """gray_windows (B, F, T, S, S) float32 in [0,1]; rgb_frames (B*F, 3, 224, 224) float32
+        (0-255 minus mean).  Both on the GPU.  Returns (B, F, 2) = [valence, arousal]; one GRU
+        sequence of length B, exactly as one reference forward with batch B."""
+        with torch.no_grad():
+            b, f = gray_windows.shape[0], gray_windows.shape[1]
+            phase_0, phase_1 = self.phase_diff_output(gray_windows, self.phase_difference_extractor)
+            feats = self.resnet50_extractor.features(rgb_frames).view(b, f, 2048)
+            return self.model([phase_0, phase_1], feats)
+
+
+def stitch_predictions(names, ranges, preds):
+    """Per-video stitching of snippet predictions (api/tester.py:104-118): later snippets overwrite the
+    overlap; asserts full coverage [0, max_len)."""
+    out = {}
+    for video in names:
+        if video in out:
+            continue
+        mask = names == video
+        v_ranges, v_preds = ranges[mask], preds[mask]
+        max_len = max(r[-1] for r in v_ranges)
+        arr = np.zeros((max_len, preds.shape[-1]))
+        lo, hi = 0, 0
+        for (start, end), p in zip(v_ranges, v_preds):
+            arr[start:end, :] = p
+            lo, hi = min(lo, start), max(hi, end)
+        assert lo == 0 and hi == max_len
+        out[video] = arr
+    return out

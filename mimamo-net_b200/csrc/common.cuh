@@ -1,0 +1,46 @@
+// Shared host-side plumbing for libmimamo_b200.so: error channel, launch counter, checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/mimamo_b200.h"
+
+namespace mimamo {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define MM_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::mimamo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MIMAMO_E_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+#define MM_REQUIRE(cond, code, ...)                                                      \
+  do {                                                                                   \
+    if (!(cond)) { ::mimamo::set_error(__VA_ARGS__); return (code); }                    \
+  } while (0)
+
+// after a kernel launch: surface launch-configuration errors without synchronising
+#define MM_LAUNCH_OK()                                                                   \
+  do {                                                                                   \
+    ::mimamo::count_launch();                                                            \
+    MM_CUDA(cudaPeekAtLastError());                                                      \
+  } while (0)
+
+template <typename T>
+inline int upload(T** dev, const T* host, size_t count) {
+  MM_CUDA(cudaMalloc((void**)dev, count * sizeof(T)));
+  MM_CUDA(cudaMemcpy(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return MIMAMO_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace mimamo

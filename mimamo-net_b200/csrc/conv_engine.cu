@@ -1,0 +1,538 @@
+// tcgen05 implicit-GEMM convolution engine for sm_100a.
+//
+// One persistent, warp-specialised kernel serves every convolution on the hot path
+// (ResNet50's 1x1 / 3x3 / strided layers, api/resnet50_extractor.py:81, and PhaseNet's 3x3
+// layers, api/mimamo_net.py:68-90):
+//
+//   warp 0      TMA producer: per K-block one activation box + one weight box into a ring of
+//               128B-swizzled shared-memory stages (mbarrier full/empty pipeline).  A 3x3 tap
+//               is just a shifted 4-D box over the NHWC activation tensor; TMA's out-of-bounds
+//               zero fill IS the convolution padding, and its element strides implement
+//               stride-2 layers, so no im2col buffer exists for any 1x1 / 3x3 layer.
+//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, fp32
+//               accumulators in TMEM, double buffered so tile i+1 overlaps tile i's epilogue).
+//   warps 2-5   epilogue: tcgen05.ld TMEM -> registers, folded-BatchNorm scale/shift,
+//               optional residual add + ReLU, 16-bit NHWC store.
+//
+// D[M = output pixels][N = Cout] = A[M][K] * B[N][K]^T,  K = taps * Cin_p (K-major, 16-bit).
+#include "common.cuh"
+#include "conv_engine.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <string.h>
+#include <vector>
+
+namespace mimamo {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                   // 64 x 2 B = one 128-byte swizzle atom
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;
+constexpr int kGemmThreads = 192;             // 1 TMA warp + 1 MMA warp + 4 epilogue warps
+constexpr int kUmmaK = 16;
+
+struct ConvParams {
+  int mode;                 // 0: flat rows, 1: spatial boxes
+  int M_total;              // flat: output pixels
+  int num_k_blocks, cin_blocks, taps_w;
+  int Wo, Ho, Nimg;
+  int bw, bh, bn, tiles_w, tiles_h;
+  int stride, pad;
+  int a_rows;               // rows one activation box delivers (<= 128)
+  int m_tiles, n_tiles;
+  uint32_t idesc;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  void* out;
+  int ldc, ld_res;
+  int relu;
+};
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; single thread issues on behalf of the CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (= 1, unused for swizzled K-major),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64), [46,48) version = 1 (sm_100),
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if (BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kTmemCols = 2 * BLOCK_N;          // double-buffered accumulator (128/256/512)
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 256 + 1024;
+};
+
+template <int BLOCK_N, bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------- TMA producer -------------------------------
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int c1 = 0, c2 = 0, c3 = 0;
+        if (p.mode == 0) {
+          c1 = m_tile * kBlockM;
+        } else {
+          const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
+          const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
+          c1 = tw * p.bw * p.stride - p.pad;
+          c2 = th * p.bh * p.stride - p.pad;
+          c3 = tn * p.bn;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.mode == 0) {
+            tma_load_2d(sA + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBlockK, c1);
+          } else {
+            const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+            tma_load_4d(sA + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBlockK, c1 + kw, c2 + kh, c3);
+          }
+          tma_load_2d(sB + stage * Cfg::kBStageBytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------- MMA issuer ---------------------------------
+      int stage = 0; uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * kAStageBytes));
+          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * Cfg::kBStageBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the
+            // (address >> 4) field
+            umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem stage when the MMAs retire
+          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // --------------------------------- epilogue -----------------------------------
+    const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
+    const int row = quarter * 32 + lane;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      long long pix = 0;
+      bool valid;
+      if (p.mode == 0) {
+        pix = (long long)m_tile * kBlockM + row;
+        valid = pix < p.M_total;
+      } else {
+        const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
+        const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
+        const int per_img = p.bw * p.bh;
+        const int dn = row / per_img, rem = row - dn * per_img;
+        const int dh = rem / p.bw, dw = rem - dh * p.bw;
+        const int n = tn * p.bn + dn, h = th * p.bh + dh, w = tw * p.bw + dw;
+        valid = row < p.a_rows && n < p.Nimg && h < p.Ho && w < p.Wo;
+        pix = ((long long)n * p.Ho + h) * p.Wo + w;
+      }
+      const int n0 = n_tile * BLOCK_N;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + pix * p.ldc + n0;
+      const uint16_t* rrow = p.residual ? reinterpret_cast<const uint16_t*>(p.residual) + pix * p.ld_res + n0 : nullptr;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float a = __uint_as_float(v[j]) * __ldg(p.scale + n0 + c0 + j) + __ldg(p.shift + n0 + c0 + j);
+            float b = __uint_as_float(v[j + 1]) * __ldg(p.scale + n0 + c0 + j + 1) + __ldg(p.shift + n0 + c0 + j + 1);
+            if (rrow) {
+              const float2 r = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(rrow + c0 + j));
+              a += r.x; b += r.y;
+            }
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            packed[j >> 1] = pack2<BF16>(a, b);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, ElemType elem, int rank, const void* base, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
+  EncodeTiledFn fn = encode_fn();
+  MM_REQUIRE(fn, MIMAMO_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bd[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(map, elem == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                  const_cast<void*>(base), gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MM_REQUIRE(r == CUDA_SUCCESS, MIMAMO_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box %u %u %u %u)",
+             (int)r, rank, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return MIMAMO_OK;
+}
+
+static uint32_t make_idesc(int block_n, ElemType elem) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @ [4,6); a/b format @ [7,10)/[10,13) (F16 = 0,
+  // BF16 = 1); a/b K-major (0) @ 15/16; N>>3 @ [17,23); M>>4 @ [24,29).
+  const uint32_t fmt = elem == kBF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+int out_size(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BLOCK_N, bool BF16>
+static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_gemm_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
+  const bool bf = L.elem == kBF16;
+  switch (L.block_n) {
+    case 64:  return bf ? launch_cfg<64, true>(a, b, p, s) : launch_cfg<64, false>(a, b, p, s);
+    case 128: return bf ? launch_cfg<128, true>(a, b, p, s) : launch_cfg<128, false>(a, b, p, s);
+    case 256: return bf ? launch_cfg<256, true>(a, b, p, s) : launch_cfg<256, false>(a, b, p, s);
+  }
+  set_error("unsupported BLOCK_N %d", L.block_n);
+  return MIMAMO_E_RUNTIME;
+}
+
+int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, const float* shift_host, int Cout,
+                    int Cin, int ksize, int stride, int pad, int relu, ElemType elem) {
+  MM_REQUIRE(Cout % 64 == 0, MIMAMO_E_RUNTIME, "Cout=%d must be a multiple of 64 for the tcgen05 engine", Cout);
+  L.Cin = Cin; L.Cin_p = (Cin + 63) / 64 * 64; L.Cout = Cout;
+  L.ksize = ksize; L.stride = stride; L.pad = pad; L.relu = relu; L.elem = elem;
+  L.block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  const int taps = ksize * ksize;
+  const size_t K = (size_t)taps * L.Cin_p;
+  std::vector<uint16_t> packed((size_t)Cout * K, 0);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < taps; ++t) {
+        const float v = w_host[((size_t)o * Cin + c) * taps + t];
+        uint16_t bits;
+        if (elem == kBF16) { __nv_bfloat16 h = __float2bfloat16(v); memcpy(&bits, &h, 2); }
+        else { __half h = __float2half(v); memcpy(&bits, &h, 2); }
+        packed[(size_t)o * K + (size_t)t * L.Cin_p + c] = bits;
+      }
+  MM_CUDA(cudaMalloc(&L.w_dev, packed.size() * 2));
+  MM_CUDA(cudaMemcpy(L.w_dev, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  int rc = upload(&L.scale_dev, scale_host, (size_t)Cout);
+  if (rc) return rc;
+  return upload(&L.shift_dev, shift_host, (size_t)Cout);
+}
+
+void conv_layer_free(ConvLayer& L) {
+  cudaFree(L.w_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev);
+  L.w_dev = nullptr; L.scale_dev = L.shift_dev = nullptr;
+}
+
+static int weight_map(const ConvLayer& L, CUtensorMap* map) {
+  const uint64_t K = (uint64_t)L.ksize * L.ksize * L.Cin_p;
+  const uint64_t dims[2] = {K, (uint64_t)L.Cout};
+  const uint64_t strides[1] = {K * 2};
+  const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)L.block_n};
+  const uint32_t es[2] = {1, 1};
+  return encode_map(map, L.elem, 2, L.w_dev, dims, strides, box, es);
+}
+
+static void fill_common(ConvParams& p, const ConvLayer& L, void* out, int ldc, const void* residual, int ld_res) {
+  p.idesc = make_idesc(L.block_n, L.elem);
+  p.scale = L.scale_dev; p.shift = L.shift_dev;
+  p.residual = residual; p.out = out; p.ldc = ldc; p.ld_res = ld_res; p.relu = L.relu;
+  p.n_tiles = L.Cout / L.block_n;
+  p.cin_blocks = L.Cin_p / kBlockK;
+  p.taps_w = L.ksize;
+  p.num_k_blocks = L.ksize * L.ksize * p.cin_blocks;
+  p.stride = L.stride; p.pad = L.pad;
+}
+
+int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, const void* residual, int ld_res,
+                 cudaStream_t stream) {
+  MM_REQUIRE(L.ksize == 1 && L.stride == 1 && L.pad == 0, MIMAMO_E_VALUE, "gemm_forward needs a 1x1 stride-1 layer");
+  MM_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ld_res % 8 == 0), MIMAMO_E_VALUE, "row pitches must be multiples of 8");
+  if (M == 0) return MIMAMO_OK;
+  CUtensorMap ma, mb;
+  const uint64_t dims[2] = {(uint64_t)L.Cin_p, (uint64_t)M};
+  const uint64_t strides[1] = {(uint64_t)L.Cin_p * 2};
+  const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
+  const uint32_t es[2] = {1, 1};
+  int rc = encode_map(&ma, L.elem, 2, a, dims, strides, box, es);
+  if (rc) return rc;
+  rc = weight_map(L, &mb);
+  if (rc) return rc;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  fill_common(p, L, out, ldc, residual, ld_res);
+  p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  return launch(L, ma, mb, p, stream);
+}
+
+int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc, const void* residual,
+                 int ld_res, cudaStream_t stream) {
+  if (L.ksize == 1 && L.stride == 1 && L.pad == 0)
+    return gemm_forward(L, x, B * H * W, out, ldc, residual, ld_res, stream);
+  MM_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ld_res % 8 == 0), MIMAMO_E_VALUE, "row pitches must be multiples of 8");
+  if (B == 0) return MIMAMO_OK;
+  const int Ho = out_size(H, L.ksize, L.stride, L.pad), Wo = out_size(W, L.ksize, L.stride, L.pad);
+  // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows
+  int best_bw = 1, best_bh = 1, best_bn = 1;
+  long long best_tiles = -1;
+  for (int bw = 1; bw <= Wo && bw <= 128; ++bw) {
+    if (bw * L.stride > 256) break;
+    for (int bh = 1; bh <= Ho && bw * bh <= 128; ++bh) {
+      if (bh * L.stride > 256) break;
+      int bn = 1;
+      if (bw == Wo && bh == Ho) { bn = 128 / (bw * bh); if (bn > B) bn = B; if (bn < 1) bn = 1; }
+      const long long tiles = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + bn - 1) / bn);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && bw > best_bw)) {
+        best_tiles = tiles; best_bw = bw; best_bh = bh; best_bn = bn;
+      }
+    }
+  }
+  CUtensorMap ma, mb;
+  const uint64_t dims[4] = {(uint64_t)L.Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)L.Cin_p * 2, (uint64_t)W * L.Cin_p * 2, (uint64_t)H * W * L.Cin_p * 2};
+  const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(best_bw * L.stride), (uint32_t)(best_bh * L.stride), (uint32_t)best_bn};
+  const uint32_t es[4] = {1, (uint32_t)L.stride, (uint32_t)L.stride, 1};
+  int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
+  if (rc) return rc;
+  rc = weight_map(L, &mb);
+  if (rc) return rc;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  fill_common(p, L, out, ldc, residual, ld_res);
+  p.mode = 1;
+  p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
+  p.bw = best_bw; p.bh = best_bh; p.bn = best_bn;
+  p.tiles_w = (Wo + best_bw - 1) / best_bw;
+  p.tiles_h = (Ho + best_bh - 1) / best_bh;
+  p.a_rows = best_bw * best_bh * best_bn;
+  p.m_tiles = (int)best_tiles;
+  return launch(L, ma, mb, p, stream);
+}
+
+}  // namespace mimamo
+
+using namespace mimamo;
+
+// Test hook (include/mimamo_b200.h): one convolution through the engine, bf16 NHWC in/out.
+extern "C" int mimamo_conv_bf16(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w_host,
+                                const float* scale_host, const float* shift_host, int32_t Cout, int32_t ksize,
+                                int32_t stride, int32_t pad, int32_t relu, const void* residual, void* out, void* stream) {
+  MM_REQUIRE(x && w_host && scale_host && shift_host && out, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(Cin % 64 == 0, MIMAMO_E_VALUE, "test hook needs Cin %% 64 == 0 (input pitch == padded Cin)");
+  ConvLayer L;
+  int rc = conv_layer_init(L, w_host, scale_host, shift_host, Cout, Cin, ksize, stride, pad, relu, kBF16);
+  if (rc == MIMAMO_OK) rc = conv_forward(L, x, B, H, W, out, Cout, residual, Cout, (cudaStream_t)stream);
+  if (rc == MIMAMO_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    set_error("conv kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = MIMAMO_E_CUDA;
+  }
+  conv_layer_free(L);
+  return rc;
+}

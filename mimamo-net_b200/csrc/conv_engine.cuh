@@ -1,0 +1,47 @@
+// tcgen05 implicit-GEMM convolution engine (sm_100a): declarations shared by resnet50.cu / head.cu.
+//
+// Replaces every cuDNN / cuBLAS convolution the reference issues through nn.Conv2d
+// (ResNet50: api/resnet50_extractor.py:81; PhaseNet: api/mimamo_net.py:84-90).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
+namespace mimamo {
+
+enum ElemType { kBF16 = 0, kF16 = 1 };
+
+// One convolution (or plain GEMM) lowered to D[M=pixels][N=Cout] = A[M][K] * B[N][K]^T with
+// K = taps * Cin_p, all operands 16-bit K-major, fp32 accumulation in TMEM.
+struct ConvLayer {
+  // static description
+  int Cin = 0, Cin_p = 0;        // logical / padded (multiple of 64) input channels
+  int Cout = 0;
+  int ksize = 1, stride = 1, pad = 0;
+  int relu = 0;
+  ElemType elem = kBF16;
+  void* w_dev = nullptr;         // [Cout][taps*Cin_p] 16-bit
+  float* scale_dev = nullptr;    // [Cout]  (eval BatchNorm folded, or ones)
+  float* shift_dev = nullptr;    // [Cout]
+  int block_n = 64;
+};
+
+// pack torch-layout fp32 weights [Cout][Cin][k][k] into the engine layout and upload.
+int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, const float* shift_host,
+                    int Cout, int Cin, int ksize, int stride, int pad, int relu, ElemType elem);
+void conv_layer_free(ConvLayer& L);
+
+// x: NHWC 16-bit [B][H][W][Cin_p] (row pitch == Cin_p).  out: NHWC 16-bit, row pitch `ldc` elements,
+// written at channel offset 0 of `out` (pass out + offset for concatenation).  residual: optional,
+// same geometry as out with pitch ld_res.  Returns MIMAMO_OK or an error code.
+int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc,
+                 const void* residual, int ld_res, cudaStream_t stream);
+
+// Plain GEMM view of the same kernel: A [M][K_p] 16-bit row-major (K_p multiple of 64).
+int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, const void* residual,
+                 int ld_res, cudaStream_t stream);
+
+int out_size(int in, int k, int s, int p);
+
+}  // namespace mimamo

@@ -1,0 +1,183 @@
+// H: two-stream head (MLP || PhaseNet -> transform -> 2-layer bidirectional GRU -> classifier).
+//
+// Replaces Two_Stream_RNN.forward in eval mode (api/mimamo_net.py:129-143; MLP :22-26, PhaseNet
+// :79-95).  Dropout layers are identities and every BatchNorm is folded into a per-channel affine.
+// PhaseNet's six 3x3 convolutions (99 % of the head's flops) run on the tcgen05 engine in fp16
+// (10-bit mantissa: the 1e-3 valence/arousal budget leaves no room for bf16 here); the stride-2
+// layers use TMA element strides, the level-1 skip concat (mimamo_net.py:85) is a channel offset
+// into a shared NHWC buffer.  The small dense layers and the GRU stay in fp32.
+#include "common.cuh"
+#include "conv_engine.cuh"
+#include "nn_kernels.cuh"
+#include "tensor_table.cuh"
+
+using namespace mimamo;
+
+struct mimamo_head {
+  int num_phase = 12, cin0 = 24;
+  ConvLayer conv[6];                      // conv_net.{0,1,2}.{0,3}
+  LinearLayer mlp1, mlp2, fc0, fc4, transform, xproj[2], classifier;
+  float* whhT[2] = {nullptr, nullptr};    // [2 dir][128][384] per layer
+  float* bhh[2] = {nullptr, nullptr};     // [2 dir][384] per layer
+  int conv_chunk = 1024;                  // windows per PhaseNet pass
+};
+
+static const ElemType kHeadElem = kF16;
+
+static int make_phase_conv(const TensorTable& T, const std::string& conv, const std::string& bn, int cout, int cin,
+                           int stride, ConvLayer& L) {
+  const float* w = T.get(conv + ".weight", (int64_t)cout * cin * 9);
+  const float* b = T.get(conv + ".bias", cout);
+  if (!w || !b) return MIMAMO_E_VALUE;
+  std::vector<float> sc, sh;
+  if (!fold_bn(T, bn, cout, 1e-5f, b, sc, sh)) return MIMAMO_E_VALUE;
+  return conv_layer_init(L, w, sc.data(), sh.data(), cout, cin, 3, stride, 1, 1, kHeadElem);
+}
+
+// Linear -> BN -> ReLU (bn_first) or Linear -> ReLU -> BN, or plain Linear (+BN)
+static int make_linear(const TensorTable& T, const std::string& lin, const std::string& bn, int out_f, int in_f, int relu,
+                       bool bn_first, LinearLayer& L) {
+  const float* w = T.get(lin + ".weight", (int64_t)out_f * in_f);
+  const float* b = T.get(lin + ".bias", out_f);
+  if (!w || !b) return MIMAMO_E_VALUE;
+  std::vector<float> sc, sh;
+  if (!bn.empty() && !fold_bn(T, bn, out_f, 1e-5f, nullptr, sc, sh)) return MIMAMO_E_VALUE;
+  const float* s = bn.empty() ? nullptr : sc.data();
+  const float* t = bn.empty() ? nullptr : sh.data();
+  return bn_first ? linear_init(L, w, b, out_f, in_f, relu, s, t, nullptr, nullptr)
+                  : linear_init(L, w, b, out_f, in_f, relu, nullptr, nullptr, s, t);
+}
+
+extern "C" void mimamo_head_destroy(mimamo_head* h) {
+  if (!h) return;
+  for (auto& c : h->conv) conv_layer_free(c);
+  linear_free(h->mlp1); linear_free(h->mlp2); linear_free(h->fc0); linear_free(h->fc4);
+  linear_free(h->transform); linear_free(h->xproj[0]); linear_free(h->xproj[1]); linear_free(h->classifier);
+  for (int l = 0; l < 2; ++l) { cudaFree(h->whhT[l]); cudaFree(h->bhh[l]); }
+  delete h;
+}
+
+extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_phase,
+                                  mimamo_head** head_out) {
+  MM_REQUIRE(tensors && head_out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(num_phase == 12, MIMAMO_E_RUNTIME, "only num_phase=12 (24 phase channels) is supported");
+  TensorTable T{tensors, n_tensors};
+  mimamo_head* h = new mimamo_head();
+  h->num_phase = num_phase; h->cin0 = 2 * num_phase;
+  const int c0 = h->cin0;
+  int rc = make_linear(T, "mlp.mlp.1", "mlp.mlp.2", 256, 2048, 1, true, h->mlp1);
+  if (!rc) rc = make_linear(T, "mlp.mlp.5", "mlp.mlp.6", 256, 256, 1, true, h->mlp2);
+  const int chans[3][2] = {{c0, 64}, {c0 + 64, 128}, {128, 256}};
+  for (int b = 0; b < 3 && !rc; ++b) {
+    char p[64];
+    snprintf(p, sizeof(p), "phasenet.conv_net.%d.", b);
+    const std::string pre(p);
+    rc = make_phase_conv(T, pre + "0", pre + "1", chans[b][1], chans[b][0], 1, h->conv[2 * b]);
+    if (!rc) rc = make_phase_conv(T, pre + "3", pre + "4", chans[b][1], chans[b][1], 2, h->conv[2 * b + 1]);
+  }
+  if (!rc) rc = make_linear(T, "phasenet.fc.0", "phasenet.fc.2", 256, 256, 1, false, h->fc0);
+  if (!rc) rc = make_linear(T, "phasenet.fc.4", "phasenet.fc.6", 256, 256, 1, false, h->fc4);
+  if (!rc) rc = make_linear(T, "transform.0", "transform.2", 256, 512, 1, false, h->transform);
+  if (!rc) rc = make_linear(T, "classifier.1", "classifier.2", 2, 256, 0, true, h->classifier);
+  for (int l = 0; l < 2 && !rc; ++l) {
+    // stack both directions' input projections into one [768][256] linear; transpose W_hh
+    std::vector<float> wih((size_t)768 * 256), bih(768), whhT((size_t)2 * 128 * 384), bhh(768);
+    for (int d = 0; d < 2 && !rc; ++d) {
+      char sfx[32];
+      snprintf(sfx, sizeof(sfx), "_l%d%s", l, d ? "_reverse" : "");
+      const float* wi = T.get(std::string("rnns.weight_ih") + sfx, 384 * 256);
+      const float* wh = T.get(std::string("rnns.weight_hh") + sfx, 384 * 128);
+      const float* bi = T.get(std::string("rnns.bias_ih") + sfx, 384);
+      const float* bh = T.get(std::string("rnns.bias_hh") + sfx, 384);
+      if (!wi || !wh || !bi || !bh) { rc = MIMAMO_E_VALUE; break; }
+      memcpy(&wih[(size_t)d * 384 * 256], wi, sizeof(float) * 384 * 256);
+      memcpy(&bih[d * 384], bi, sizeof(float) * 384);
+      memcpy(&bhh[d * 384], bh, sizeof(float) * 384);
+      for (int g = 0; g < 384; ++g)
+        for (int k = 0; k < 128; ++k) whhT[((size_t)d * 128 + k) * 384 + g] = wh[(size_t)g * 128 + k];
+    }
+    if (!rc) rc = linear_init(h->xproj[l], wih.data(), bih.data(), 768, 256, 0, nullptr, nullptr, nullptr, nullptr);
+    if (!rc) rc = upload(&h->whhT[l], whhT.data(), whhT.size());
+    if (!rc) rc = upload(&h->bhh[l], bhh.data(), bhh.size());
+  }
+  if (rc) { mimamo_head_destroy(h); return rc; }
+  *head_out = h;
+  return MIMAMO_OK;
+}
+
+namespace {
+struct HeadLayout {
+  size_t feat, f2, xp, y0, y1, pool, fc, a0, a1, cat, a2, a3, a4, a5, total;
+};
+HeadLayout head_layout(const mimamo_head* h, int M) {
+  HeadLayout L;
+  size_t cur = 0;
+  auto take = [&](size_t bytes) { size_t at = cur; cur += align_up(bytes, 1024); return at; };
+  const size_t Mc = (size_t)(M < h->conv_chunk ? M : h->conv_chunk);
+  L.feat = take((size_t)M * 512 * 4);
+  L.f2 = take((size_t)M * 256 * 4);
+  L.xp = take((size_t)M * 768 * 4);
+  L.y0 = take((size_t)M * 256 * 4);
+  L.y1 = take((size_t)M * 256 * 4);
+  L.pool = take((size_t)M * 256 * 4);
+  L.fc = take((size_t)M * 256 * 4);
+  L.a0 = take(Mc * 48 * 48 * 64 * 2);     // phase_0 as NHWC (24 -> 64 channels)
+  L.a1 = take(Mc * 48 * 48 * 64 * 2);     // conv_net[0][0]
+  L.cat = take(Mc * 24 * 24 * 128 * 2);   // [conv_net[0][3] (64) | phase_1 (24) | zero pad]
+  L.a2 = take(Mc * 24 * 24 * 128 * 2);    // conv_net[1][0]
+  L.a3 = take(Mc * 12 * 12 * 128 * 2);    // conv_net[1][3]
+  L.a4 = take(Mc * 12 * 12 * 256 * 2);    // conv_net[2][0]
+  L.a5 = take(Mc * 6 * 6 * 256 * 2);      // conv_net[2][3]
+  L.total = cur + 1024;
+  return L;
+}
+}  // namespace
+
+extern "C" int mimamo_head_workspace_bytes(const mimamo_head* head, int32_t bs, int32_t nf, size_t* bytes_out) {
+  MM_REQUIRE(head && bytes_out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
+  *bytes_out = head_layout(head, bs * nf > 0 ? bs * nf : 1).total;
+  return MIMAMO_OK;
+}
+
+extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, const float* phase_1, const float* rgb,
+                                   int32_t bs, int32_t nf, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  MM_REQUIRE(h && phase_0 && phase_1 && rgb && out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
+  const int M = bs * nf;
+  if (M == 0) return MIMAMO_OK;
+  cudaStream_t s = (cudaStream_t)stream_;
+  const HeadLayout L = head_layout(h, M);
+  MM_REQUIRE(workspace && workspace_bytes >= L.total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", L.total);
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  float* feat = (float*)(ws + L.feat); float* f2 = (float*)(ws + L.f2); float* xp = (float*)(ws + L.xp);
+  float* y0 = (float*)(ws + L.y0); float* y1 = (float*)(ws + L.y1); float* pool = (float*)(ws + L.pool);
+  float* fc = (float*)(ws + L.fc);
+  // spatial stream: MLP over the ResNet50 features -> feat[:, 0:256]
+  int rc = linear_forward(h->mlp1, rgb, 2048, M, f2, 256, s);
+  if (!rc) rc = linear_forward(h->mlp2, f2, 256, M, feat, 512, s);
+  // temporal stream: PhaseNet -> feat[:, 256:512]
+  const int c0 = h->cin0;
+  for (int m0 = 0; m0 < M && !rc; m0 += h->conv_chunk) {
+    const int Mc = M - m0 < h->conv_chunk ? M - m0 : h->conv_chunk;
+    void* a0 = ws + L.a0; void* a1 = ws + L.a1; void* cat = ws + L.cat; void* a2 = ws + L.a2;
+    void* a3 = ws + L.a3; void* a4 = ws + L.a4; void* a5 = ws + L.a5;
+    rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
+    if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
+    if (!rc) rc = conv_forward(h->conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
+    if (!rc) rc = conv_forward(h->conv[1], a1, Mc, 48, 48, cat, 128, nullptr, 0, s);      // -> cat[..., 0:64], 24x24
+    if (!rc) rc = conv_forward(h->conv[2], cat, Mc, 24, 24, a2, 128, nullptr, 0, s);
+    if (!rc) rc = conv_forward(h->conv[3], a2, Mc, 24, 24, a3, 128, nullptr, 0, s);       // 12x12
+    if (!rc) rc = conv_forward(h->conv[4], a3, Mc, 12, 12, a4, 256, nullptr, 0, s);
+    if (!rc) rc = conv_forward(h->conv[5], a4, Mc, 12, 12, a5, 256, nullptr, 0, s);       // 6x6
+    if (!rc) rc = avgpool_to_f32(a5, Mc, 36, 256, pool + (size_t)m0 * 256, 256, 0, kHeadElem, s);
+  }
+  if (!rc) rc = linear_forward(h->fc0, pool, 256, M, fc, 256, s);
+  if (!rc) rc = linear_forward(h->fc4, fc, 256, M, feat + 256, 512, s);
+  // fusion + recurrence over dim 0 (= bs; the nf frames are the GRU batch)
+  if (!rc) rc = linear_forward(h->transform, feat, 512, M, f2, 256, s);
+  if (!rc) rc = linear_forward(h->xproj[0], f2, 256, M, xp, 768, s);
+  if (!rc) rc = gru_layer(xp, h->whhT[0], h->bhh[0], bs, nf, 128, y0, s);
+  if (!rc) rc = linear_forward(h->xproj[1], y0, 256, M, xp, 768, s);
+  if (!rc) rc = gru_layer(xp, h->whhT[1], h->bhh[1], bs, nf, 128, y1, s);
+  if (!rc) rc = linear_forward(h->classifier, y1, 256, M, out, 2, s);
+  return rc;
+}

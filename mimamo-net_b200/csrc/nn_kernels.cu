@@ -1,0 +1,314 @@
+#include "common.cuh"
+#include "nn_kernels.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace mimamo {
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t to16(float v) {
+  if (BF16) { __nv_bfloat16 h = __float2bfloat16(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __half h = __float2half(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+template <bool BF16>
+__device__ __forceinline__ float from16(uint16_t u) {
+  if (BF16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<__half*>(&u));
+}
+
+// ---- NCHW fp32 -> NHWC 16-bit (8 channels = one 16-byte store per thread) -------------------
+template <bool BF16>
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ src, long long N, int C, int H, int W,
+                                      uint16_t* __restrict__ dst, int ldc, int c_off, int groups) {
+  const long long total = N * H * (long long)groups * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int g = (int)(r % groups); r /= groups;
+    const int h = (int)(r % H);
+    const long long n = r / H;
+    uint16_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      v[j] = c < C ? to16<BF16>(__ldg(src + ((n * C + c) * H + h) * (long long)W + w)) : (uint16_t)0;
+    }
+    uint4 o;
+    o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+    o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+    *reinterpret_cast<uint4*>(dst + ((n * H + h) * (long long)W + w) * ldc + c_off + g * 8) = o;
+  }
+}
+
+int nchw_to_nhwc16(const float* src, int N, int C, int H, int W, void* dst, int ldc, int c_off, int c_fill,
+                   ElemType elem, cudaStream_t s) {
+  MM_REQUIRE(c_off % 8 == 0 && c_fill % 8 == 0 && ldc % 8 == 0 && c_fill >= C, MIMAMO_E_VALUE, "nchw_to_nhwc16: channel geometry must be 8-aligned");
+  if (N == 0) return MIMAMO_OK;
+  const int groups = c_fill / 8;
+  const long long total = (long long)N * H * groups * W;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  if (elem == kBF16) nchw_to_nhwc16_kernel<true><<<grid, 256, 0, s>>>(src, N, C, H, W, (uint16_t*)dst, ldc, c_off, groups);
+  else nchw_to_nhwc16_kernel<false><<<grid, 256, 0, s>>>(src, N, C, H, W, (uint16_t*)dst, ldc, c_off, groups);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// ---- conv1 im2col -------------------------------------------------------------------------
+template <bool BF16>
+__global__ void im2col_conv1_kernel(const float* __restrict__ x, long long B, uint16_t* __restrict__ a) {
+  // one thread: 8 consecutive K entries (16 B) of one output pixel; K = c*49 + kh*7 + kw, 147 -> 192
+  const long long total = B * 112 * 112 * 24;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % 24);
+    const long long pix = i / 24;
+    const int wo = (int)(pix % 112);
+    const int ho = (int)((pix / 112) % 112);
+    const long long b = pix / (112 * 112);
+    uint16_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
+        const int hi = ho * 2 + kh - 3, wi = wo * 2 + kw - 3;
+        if (hi >= 0 && hi < 224 && wi >= 0 && wi < 224) val = __ldg(x + ((b * 3 + c) * 224 + hi) * 224ll + wi);
+      }
+      v[j] = to16<BF16>(val);
+    }
+    uint4 o;
+    o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+    o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+    *reinterpret_cast<uint4*>(a + pix * 192 + g * 8) = o;
+  }
+}
+
+int im2col_conv1(const float* x, int B, void* a, ElemType elem, cudaStream_t s) {
+  if (B == 0) return MIMAMO_OK;
+  const int grid = 148 * 16;
+  if (elem == kBF16) im2col_conv1_kernel<true><<<grid, 256, 0, s>>>(x, B, (uint16_t*)a);
+  else im2col_conv1_kernel<false><<<grid, 256, 0, s>>>(x, B, (uint16_t*)a);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// ---- max pool 3x3 s2 ceil_mode --------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  if (BF16) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <bool BF16>
+__global__ void maxpool_kernel(const uint4* __restrict__ x, long long B, int H, int W, int C8, int Ho, int Wo,
+                               uint4* __restrict__ out) {
+  const long long total = B * Ho * Wo * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long b = r / Ho;
+    uint4 m;
+    bool first = true;
+    for (int dh = 0; dh < 3; ++dh) {
+      const int h = ho * 2 + dh;
+      if (h >= H) break;
+      for (int dw = 0; dw < 3; ++dw) {
+        const int w = wo * 2 + dw;
+        if (w >= W) break;
+        const uint4 v = __ldg(x + ((b * H + h) * W + w) * C8 + c);
+        if (first) { m = v; first = false; }
+        else { m.x = max2<BF16>(m.x, v.x); m.y = max2<BF16>(m.y, v.y); m.z = max2<BF16>(m.z, v.z); m.w = max2<BF16>(m.w, v.w); }
+      }
+    }
+    out[i] = m;
+  }
+}
+
+int maxpool3x3s2_ceil(const void* x, int B, int H, int W, int C, void* out, ElemType elem, cudaStream_t s) {
+  MM_REQUIRE(C % 8 == 0, MIMAMO_E_VALUE, "maxpool: C must be a multiple of 8");
+  if (B == 0) return MIMAMO_OK;
+  const int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;      // ceil((H-3)/2) + 1
+  const int grid = 148 * 16;
+  if (elem == kBF16) maxpool_kernel<true><<<grid, 256, 0, s>>>((const uint4*)x, B, H, W, C / 8, Ho, Wo, (uint4*)out);
+  else maxpool_kernel<false><<<grid, 256, 0, s>>>((const uint4*)x, B, H, W, C / 8, Ho, Wo, (uint4*)out);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// ---- global average pool ---------------------------------------------------------------------
+template <bool BF16>
+__global__ void avgpool_kernel(const uint16_t* __restrict__ x, long long N, int HW, int C, float* __restrict__ out,
+                               int ldo, int relu) {
+  const long long total = N * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long n = i / C;
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += from16<BF16>(__ldg(x + (n * HW + p) * C + c));
+    acc /= (float)HW;
+    if (relu) acc = fmaxf(acc, 0.f);
+    out[n * ldo + c] = acc;
+  }
+}
+
+int avgpool_to_f32(const void* x, int N, int HW, int C, float* out, int ldo, int relu, ElemType elem, cudaStream_t s) {
+  if (N == 0) return MIMAMO_OK;
+  const long long total = (long long)N * C;
+  const int grid = (int)((total + 255) / 256);
+  if (elem == kBF16) avgpool_kernel<true><<<grid, 256, 0, s>>>((const uint16_t*)x, N, HW, C, out, ldo, relu);
+  else avgpool_kernel<false><<<grid, 256, 0, s>>>((const uint16_t*)x, N, HW, C, out, ldo, relu);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// ---- fp32 linear layer (head MLP / FC / GRU input projections; ~1.4 MMAC per window) ---------
+constexpr int kLinTile = 64, kLinK = 16;
+
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ a, int lda, int M, const float* __restrict__ w, int K, int N,
+              const float* __restrict__ bias, const float* __restrict__ pre_s, const float* __restrict__ pre_t,
+              const float* __restrict__ post_s, const float* __restrict__ post_t, int relu, float* __restrict__ out, int ldo) {
+  __shared__ float As[kLinK][kLinTile + 4];
+  __shared__ float Ws[kLinK][kLinTile + 4];
+  const int m0 = blockIdx.y * kLinTile, n0 = blockIdx.x * kLinTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += kLinK) {
+    for (int i = threadIdx.x; i < kLinTile * kLinK; i += 256) {
+      const int r = i / kLinK, kk = i - r * kLinK;
+      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+      As[kk][r] = (m < M && k < K) ? __ldg(a + (size_t)m * lda + k) : 0.f;
+      Ws[kk][r] = (n < N && k < K) ? __ldg(w + (size_t)n * K + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kLinK; ++kk) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; wv[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (pre_s) v = v * pre_s[n] + pre_t[n];
+      if (relu) v = fmaxf(v, 0.f);
+      if (post_s) v = v * post_s[n] + post_t[n];
+      out[(size_t)m * ldo + n] = v;
+    }
+  }
+}
+
+static int up_opt(float** dst, const float* src, size_t n) {
+  *dst = nullptr;
+  if (!src) return MIMAMO_OK;
+  return upload(dst, src, n);
+}
+
+int linear_init(LinearLayer& L, const float* w, const float* bias, int out_f, int in_f, int relu, const float* pre_s,
+                const float* pre_t, const float* post_s, const float* post_t) {
+  L.in_f = in_f; L.out_f = out_f; L.relu = relu;
+  int rc = upload(&L.w, w, (size_t)out_f * in_f);
+  if (!rc) rc = up_opt(&L.bias, bias, out_f);
+  if (!rc) rc = up_opt(&L.pre_s, pre_s, out_f);
+  if (!rc) rc = up_opt(&L.pre_t, pre_t, out_f);
+  if (!rc) rc = up_opt(&L.post_s, post_s, out_f);
+  if (!rc) rc = up_opt(&L.post_t, post_t, out_f);
+  return rc;
+}
+
+void linear_free(LinearLayer& L) {
+  cudaFree(L.w); cudaFree(L.bias); cudaFree(L.pre_s); cudaFree(L.pre_t); cudaFree(L.post_s); cudaFree(L.post_t);
+  L = LinearLayer();
+}
+
+int linear_forward(const LinearLayer& L, const float* a, int lda, int M, float* out, int ldo, cudaStream_t s) {
+  if (M == 0) return MIMAMO_OK;
+  dim3 grid((L.out_f + kLinTile - 1) / kLinTile, (M + kLinTile - 1) / kLinTile);
+  linear_kernel<<<grid, 256, 0, s>>>(a, lda, M, L.w, L.in_f, L.out_f, L.bias, L.pre_s, L.pre_t, L.post_s, L.post_t,
+                                     L.relu, out, ldo);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// ---- GRU recurrence ---------------------------------------------------------------------------
+// The reference builds nn.GRU without batch_first (api/mimamo_net.py:119) and feeds (bs, frames, 256),
+// so the recurrence runs over dim 0 (snippets) and the 64 frames are independent batch rows
+// (SURVEY.md section 0.2).  One CTA owns kGruRows batch rows of one direction for the whole
+// sequence (persistent over time); thread j owns hidden unit j.  Gate order r, z, n as in torch.
+constexpr int kGruRows = 4;
+
+__global__ void __launch_bounds__(128)
+gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, const float* __restrict__ bhh, int S, int Bt,
+           float* __restrict__ y) {
+  constexpr int Hd = 128, G = 3 * Hd;
+  __shared__ float h[2][kGruRows][Hd];
+  const int dir = blockIdx.y, j = threadIdx.x;
+  const int row0 = blockIdx.x * kGruRows;
+  const float* W = whhT + (size_t)dir * Hd * G;
+  const float br = bhh[dir * G + j], bz = bhh[dir * G + Hd + j], bn = bhh[dir * G + 2 * Hd + j];
+  for (int r = 0; r < kGruRows; ++r) h[0][r][j] = 0.f;
+  __syncthreads();
+  int cur = 0;
+  for (int step = 0; step < S; ++step) {
+    const int s = dir == 0 ? step : S - 1 - step;
+    float ar[kGruRows], az[kGruRows], an[kGruRows];
+#pragma unroll
+    for (int r = 0; r < kGruRows; ++r) { ar[r] = br; az[r] = bz; an[r] = bn; }
+#pragma unroll 4
+    for (int k = 0; k < Hd; ++k) {
+      const float wr = __ldg(W + (size_t)k * G + j), wz = __ldg(W + (size_t)k * G + Hd + j), wn = __ldg(W + (size_t)k * G + 2 * Hd + j);
+#pragma unroll
+      for (int r = 0; r < kGruRows; ++r) {
+        const float hv = h[cur][r][k];
+        ar[r] = fmaf(hv, wr, ar[r]); az[r] = fmaf(hv, wz, az[r]); an[r] = fmaf(hv, wn, an[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kGruRows; ++r) {
+      const int row = row0 + r;
+      if (row < Bt) {
+        const float* xp = xproj + (((size_t)s * Bt + row) * 2 + dir) * G;
+        const float rg = 1.f / (1.f + expf(-(xp[j] + ar[r])));
+        const float zg = 1.f / (1.f + expf(-(xp[Hd + j] + az[r])));
+        const float ng = tanhf(xp[2 * Hd + j] + rg * an[r]);
+        const float hn = (1.f - zg) * ng + zg * h[cur][r][j];
+        h[cur ^ 1][r][j] = hn;
+        y[((size_t)s * Bt + row) * (2 * Hd) + dir * Hd + j] = hn;
+      } else {
+        h[cur ^ 1][r][j] = 0.f;
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+int gru_layer(const float* xproj, const float* whhT, const float* bhh, int S, int Bt, int Hd, float* y, cudaStream_t s) {
+  MM_REQUIRE(Hd == 128, MIMAMO_E_RUNTIME, "GRU kernel is specialised for hidden size 128");
+  if (S == 0 || Bt == 0) return MIMAMO_OK;
+  dim3 grid((Bt + kGruRows - 1) / kGruRows, 2);
+  gru_kernel<<<grid, 128, 0, s>>>(xproj, whhT, bhh, S, Bt, y);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+}  // namespace mimamo

@@ -1,0 +1,285 @@
+// P2: phase tail -- atan2, magnitude, temporal unwrap, amplitude-weighted Gaussian blur,
+// temporal difference, spatial-mean removal, clamp -- in ONE pass over the coefficients.
+//
+// Replaces Phase_Difference_Extractor.extract (api/phase_difference_extractor.py:93-134) and its
+// helpers torch_unwrap / torch_diff / amplitude_based_gaussian_blur / gaussian_kernel
+// (api/utils/phase_utils.py:5-40,78-90,108-115): ~20 elementwise passes, two cuDNN depthwise
+// convolutions and a device sync in the reference; here each coefficient is read once and each
+// phase-difference value written once (twice when a map is split into tiles).
+//
+// One CTA owns a spatial tile of one (window, band) map and walks the T frames in order, keeping
+// the per-pixel unwrap state (previous raw phase, running correction) and the previous blurred
+// frame in shared memory.  The 11x11 kernel exp(-(x^2+y^2)/8) is separable, so the blur is an
+// 11-tap row pass followed by an 11-tap column pass over zero-padded tiles.
+#include "common.cuh"
+#include <math.h>
+
+namespace mimamo {
+
+constexpr int kTailThreads = 256;
+constexpr int kHalo = 5;          // (11 - 1) / 2
+constexpr int kTaps = 11;
+constexpr int kWholeMapMax = 56;  // maps up to 56x56 are handled by a single CTA
+constexpr int kTile = 32;
+
+__constant__ float c_gauss[kTaps];
+
+struct TailGeom {
+  int T, rows, cols;
+  int tile_r, tile_c, tiles_r, tiles_c;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The reference's unwrap uses C fmod, so only jumps above +pi are corrected; the exact fp32
+// operation order of api/utils/phase_utils.py:9-17 is reproduced so residues match bit for bit.
+__device__ __forceinline__ float unwrap_correction(float dd) {
+  const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
+  float ddmod = __fsub_rn(fmodf(__fadd_rn(dd, PI_F), TWO_PI_F), PI_F);
+  if (ddmod == -PI_F && dd > 0.f) ddmod = PI_F;
+  float corr = __fsub_rn(ddmod, dd);
+  if (fabsf(dd) < PI_F) corr = 0.f;
+  return corr;
+}
+
+__global__ void __launch_bounds__(kTailThreads)
+phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
+                  const TailGeom g) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int rin = g.tile_r + 2 * kHalo, cin = g.tile_c + 2 * kHalo;
+  const int n_in = rin * cin, n_out = g.tile_r * g.tile_c;
+  double* cum = reinterpret_cast<double*>(raw);                 // [n_in] running unwrap correction
+  float* prev = reinterpret_cast<float*>(cum + n_in);            // [n_in] previous raw phase
+  float* mp = prev + n_in;                                       // [n_in] mag * unwrapped phase
+  float* mg = mp + n_in;                                         // [n_in] mag
+  float* hmp = mg + n_in;                                        // [rin][tile_c] row-blurred
+  float* hmg = hmp + rin * g.tile_c;
+  float* blur_prev = hmg + rin * g.tile_c;                       // [n_out]
+  float* delta = blur_prev + n_out;                              // [n_out]
+  __shared__ double red[kTailThreads / 32];
+  __shared__ float mean_s;
+
+  const long long map = blockIdx.x;
+  const int tile = blockIdx.y;
+  const int y0 = (tile / g.tiles_c) * g.tile_r, x0 = (tile % g.tiles_c) * g.tile_c;
+  const int th = min(g.tile_r, g.rows - y0), tw = min(g.tile_c, g.cols - x0);   // valid outputs
+  const size_t plane = (size_t)g.rows * g.cols;
+  const bool single = (g.tiles_r * g.tiles_c == 1);
+  const int ntiles = g.tiles_r * g.tiles_c;
+
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { cum[i] = 0.0; prev[i] = 0.f; }
+
+  for (int t = 0; t < g.T; ++t) {
+    const float2* src = reinterpret_cast<const float2*>(coeff) + ((size_t)map * g.T + t) * plane;
+    // (A) phase, magnitude, unwrap over time
+    for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+      const int ry = i / cin, rx = i - ry * cin;
+      const int y = y0 - kHalo + ry, x = x0 - kHalo + rx;
+      float vmp = 0.f, vmg = 0.f;                                // zero padding of F.conv2d
+      if (y >= 0 && y < g.rows && x >= 0 && x < g.cols) {
+        const float2 v = __ldg(src + (size_t)y * g.cols + x);
+        const float ph = atan2f(v.y, v.x);
+        const float mag = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+        float up = ph;
+        if (t > 0) {
+          cum[i] += (double)unwrap_correction(__fsub_rn(ph, prev[i]));   // torch CPU cumsum: double acc
+          up = __fadd_rn(ph, (float)cum[i]);
+        }
+        prev[i] = ph;
+        vmp = __fmul_rn(mag, up);
+        vmg = mag;
+      }
+      mp[i] = vmp;
+      mg[i] = vmg;
+    }
+    __syncthreads();
+    // (B) row pass
+    for (int i = threadIdx.x; i < rin * g.tile_c; i += blockDim.x) {
+      const int ry = i / g.tile_c, x = i - ry * g.tile_c;
+      const float* a = mp + ry * cin + x;
+      const float* b = mg + ry * cin + x;
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int d = 0; d < kTaps; ++d) { sa = fmaf(c_gauss[d], a[d], sa); sb = fmaf(c_gauss[d], b[d], sb); }
+      hmp[i] = sa;
+      hmg[i] = sb;
+    }
+    __syncthreads();
+    // (C) column pass, ratio, temporal difference
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+      const int y = i / g.tile_c, x = i - y * g.tile_c;
+      if (y < th && x < tw) {
+        const float* a = hmp + y * g.tile_c + x;
+        const float* b = hmg + y * g.tile_c + x;
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int d = 0; d < kTaps; ++d) { sa = fmaf(c_gauss[d], a[d * g.tile_c], sa); sb = fmaf(c_gauss[d], b[d * g.tile_c], sb); }
+        const float val = __fdiv_rn(sa, sb);
+        if (t > 0) {
+          const float dl = __fsub_rn(val, blur_prev[i]);
+          delta[i] = dl;
+          part += (double)dl;
+        }
+        blur_prev[i] = val;
+      }
+    }
+    if (t > 0) {
+      part = warp_sum(part);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < kTailThreads / 32; ++i) tot += red[i];
+        if (single) mean_s = (float)(tot / (double)plane);
+        else partial[((size_t)map * (g.T - 1) + (t - 1)) * ntiles + tile] = tot;
+      }
+      __syncthreads();
+      const float mean = single ? mean_s : 0.f;
+      const float lim = 15.7079632679489656f;                    // 5*pi
+      float* dst = out + ((size_t)map * (g.T - 1) + (t - 1)) * plane;
+      for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+        const int y = i / g.tile_c, x = i - y * g.tile_c;
+        if (y < th && x < tw) {
+          float v = delta[i];
+          if (single) v = fminf(fmaxf(__fsub_rn(v, mean), -lim), lim);
+          dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Tiled maps only: subtract the map mean (fixed-order sum of the tile partials) and clamp.
+__global__ void phase_tail_finish_kernel(float* __restrict__ out, const double* __restrict__ partial,
+                                         int ntiles, long long plane) {
+  const long long m = blockIdx.x;                       // (map, t) index
+  double tot = 0.0;
+  for (int i = 0; i < ntiles; ++i) tot += partial[m * ntiles + i];
+  const float mean = (float)(tot / (double)plane);
+  const float lim = 15.7079632679489656f;
+  float* p = out + m * plane;
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.y * blockDim.x)
+    p[i] = fminf(fmaxf(__fsub_rn(p[i], mean), -lim), lim);
+}
+
+static TailGeom make_geom(int T, int rows, int cols) {
+  TailGeom g;
+  g.T = T; g.rows = rows; g.cols = cols;
+  if (rows <= kWholeMapMax && cols <= kWholeMapMax) { g.tile_r = rows; g.tile_c = cols; }
+  else { g.tile_r = kTile; g.tile_c = kTile; }
+  g.tiles_r = (rows + g.tile_r - 1) / g.tile_r;
+  g.tiles_c = (cols + g.tile_c - 1) / g.tile_c;
+  return g;
+}
+
+static size_t tail_smem(const TailGeom& g) {
+  const size_t rin = g.tile_r + 2 * kHalo, cin = g.tile_c + 2 * kHalo;
+  return rin * cin * (sizeof(double) + 3 * sizeof(float)) + 2 * rin * g.tile_c * sizeof(float) +
+         2 * (size_t)g.tile_r * g.tile_c * sizeof(float);
+}
+
+static bool g_tail_ready = false;
+static int tail_setup() {
+  if (g_tail_ready) return MIMAMO_OK;
+  float taps[kTaps];
+  for (int d = 0; d < kTaps; ++d) taps[d] = (float)exp(-(double)((d - kHalo) * (d - kHalo)) / 8.0);   // std = 2
+  MM_CUDA(cudaMemcpyToSymbol(c_gauss, taps, sizeof(taps)));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  g_tail_ready = true;
+  return MIMAMO_OK;
+}
+
+int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, float* out,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  MM_REQUIRE(coeff && out, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "phase_extract needs T >= 2 frames and a non-empty map");
+  if (n_maps == 0) return MIMAMO_OK;
+  int rc = tail_setup();
+  if (rc) return rc;
+  const TailGeom g = make_geom(T, rows, cols);
+  const int ntiles = g.tiles_r * g.tiles_c;
+  size_t need = 0;
+  if (ntiles > 1) need = (size_t)n_maps * (T - 1) * ntiles * sizeof(double);
+  MM_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
+  MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
+  dim3 grid((unsigned)n_maps, (unsigned)ntiles);
+  phase_tail_kernel<<<grid, kTailThreads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g);
+  MM_LAUNCH_OK();
+  if (ntiles > 1) {
+    const long long plane = (long long)rows * cols;
+    dim3 fgrid((unsigned)(n_maps * (T - 1)), (unsigned)((plane + 4095) / 4096));
+    phase_tail_finish_kernel<<<fgrid, 256, 0, stream>>>(out, (const double*)workspace, ntiles, plane);
+    MM_LAUNCH_OK();
+  }
+  return MIMAMO_OK;
+}
+
+}  // namespace mimamo
+
+using namespace mimamo;
+
+extern "C" int mimamo_phase_extract_workspace_bytes(int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
+                                                    size_t* bytes_out) {
+  MM_REQUIRE(bytes_out && T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "bad geometry");
+  const TailGeom g = make_geom(T, rows, cols);
+  const int ntiles = g.tiles_r * g.tiles_c;
+  *bytes_out = ntiles > 1 ? (size_t)n_maps * (T - 1) * ntiles * sizeof(double) : 0;
+  return MIMAMO_OK;
+}
+
+extern "C" int mimamo_phase_extract(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
+                                    float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return phase_extract_launch(coeff, n_maps, T, rows, cols, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- P3: frames -> phase-difference maps (Tester.phase_diff_output, api/tester.py:122-139) ----
+extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops);
+
+static int fused_layout(const mimamo_pyr_plan* plan, int64_t n_windows, int T, size_t* coeff_off, size_t* tail_off,
+                        size_t* total, int* n_levels, int* nb, int* crops) {
+  mimamo_pyr_plan_levels(plan, n_levels, nb, crops);
+  size_t cur = 0, tail_need = 0;
+  for (int i = 0; i < *n_levels; ++i) {
+    coeff_off[i] = cur;
+    cur += align_up((size_t)n_windows * *nb * T * crops[i] * crops[i] * 2 * sizeof(float), 256);
+    size_t b = 0;
+    if (T >= 2) mimamo_phase_extract_workspace_bytes(n_windows * *nb, T, crops[i], crops[i], &b);
+    tail_need = tail_need > b ? tail_need : b;
+  }
+  *tail_off = cur;
+  *total = cur + align_up(tail_need, 256);
+  return MIMAMO_OK;
+}
+
+extern "C" int mimamo_pyr_phase_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T,
+                                                size_t* bytes_out) {
+  MM_REQUIRE(plan && bytes_out && n_windows >= 0 && T >= 2, MIMAMO_E_VALUE, "bad arguments");
+  size_t coff[MIMAMO_MAX_LEVELS], toff;
+  int nl, nb, crops[MIMAMO_MAX_LEVELS];
+  return fused_layout(plan, n_windows, T, coff, &toff, bytes_out, &nl, &nb, crops);
+}
+
+extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
+                                float* const* out, void* workspace, size_t workspace_bytes, void* stream) {
+  MM_REQUIRE(plan && frames && out && n_windows >= 0 && T >= 2, MIMAMO_E_VALUE, "bad arguments");
+  if (n_windows == 0) return MIMAMO_OK;
+  size_t coff[MIMAMO_MAX_LEVELS], toff, total;
+  int nl, nb, crops[MIMAMO_MAX_LEVELS];
+  fused_layout(plan, n_windows, T, coff, &toff, &total, &nl, &nb, crops);
+  MM_REQUIRE(workspace && workspace_bytes >= total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", total);
+  float* cptr[MIMAMO_MAX_LEVELS];
+  for (int i = 0; i < nl; ++i) cptr[i] = reinterpret_cast<float*>((char*)workspace + coff[i]);
+  int rc = mimamo_pyr_build(plan, frames, n_windows, T, cptr, stream);
+  if (rc) return rc;
+  for (int i = 0; i < nl; ++i) {
+    rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
+                              workspace_bytes - toff, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return MIMAMO_OK;
+}

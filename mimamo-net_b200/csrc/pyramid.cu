@@ -1,0 +1,337 @@
+// P0+P1: complex steerable pyramid of mirror-extended frames, one CTA per frame.
+//
+// Replaces symmetric_extension_batch (api/utils/phase_utils.py:116-129), SCFpyr_PyTorch.build /
+// _build_levels (api/steerable/SCFpyr_PyTorch.py:70-208) and the stack/permute/crop of
+// Phase_Difference_Extractor.build_pyramid (api/phase_difference_extractor.py:38-87).
+//
+// Formulation (derived in mimamo-net_b200/api/steerable/plan_tables.py): because the frame is
+// mirror-extended before the FFT, its spectrum is a real 2-D DCT-II `C` times unit phases, and
+// each oriented band collapses to four real matrix products against host-built tables:
+//
+//   Ct[l][k]      = sum_{m,n} X[m][n] dct[m][k] dct[n][l]                      (2 products)
+//   U[half][k][x] = sum_l (Ct[l][k] * mask[b][ch][half][l][k]) * trig[sel][l][x]
+//   out_ch[y][x]  = sum_{kk < 2hp} trig[kk][y] * U[kk][x]
+//
+// All operands are K-major so every product is  D[i][j] = sum_k A[k][i] B[k][j]  with float4
+// loads along i and j; the frame's spectrum, the intermediates U and the frame itself never
+// leave shared memory, and no mirrored copy / fftshift / crop is ever materialised.
+#include "common.cuh"
+
+namespace mimamo {
+
+struct LevelDev {
+  int c, h, hp, cp;
+  const float* trig;    // [2][hp][cp]
+  const float* masks;   // [nb][2][2][hp][hp]
+  int inner_sel[2][2];
+  int units_per_chunk;  // how many (band,ch) units fit the work region at once
+};
+
+struct PlanDev {
+  int H, Hp, Kp, nb, n_levels;
+  int work_floats;
+  const float* dct_t;   // [Hp][Kp]
+  LevelDev lv[MIMAMO_MAX_LEVELS];
+};
+
+struct OutPtrs { float* p[MIMAMO_MAX_LEVELS]; };
+
+constexpr int kPyrThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p, bool global) {
+  return global ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
+
+// acc[r][c] += sum_k A[k*lda + r] * (mask) * B[k*ldb + c],  r,c in [0,4)
+template <bool A_GLOBAL, bool B_GLOBAL, bool MASKED>
+__device__ __forceinline__ void tile4x4(const float* __restrict__ A, int lda,
+                                        const float* __restrict__ Mk, int ldm,
+                                        const float* __restrict__ B, int ldb, int K, float (&acc)[4][4]) {
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    float4 a = ld4(A + (size_t)k * lda, A_GLOBAL);
+    if (MASKED) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(Mk + (size_t)k * ldm));
+      a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
+    }
+    const float4 b = ld4(B + (size_t)k * ldb, B_GLOBAL);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+  }
+}
+
+__device__ __forceinline__ void zero(float (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+}
+
+__device__ __forceinline__ void store_rows(float* dst, int ld, const float (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    *reinterpret_cast<float4*>(dst + (size_t)r * ld) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+}
+
+__device__ float block_sum(float v, float* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += scratch[i];
+  __syncthreads();
+  return tot;
+}
+
+// Forward half: frame -> Ct (kept in shared memory).  Xs / R1 live in the work region.
+__device__ void frame_spectrum(const PlanDev& P, const float* __restrict__ frame, float* Ct, float* W,
+                               float* red) {
+  const int H = P.H, Hp = P.Hp, Kp = P.Kp;
+  float* Xs = W;                 // [Hp][Hp]  X[m][n], zero padded
+  float* R1 = W + Hp * Hp;       // [Hp][Kp]  R1[n][k]
+  float part = 0.f;
+  for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+    const int m = i / Hp, n = i - m * Hp;
+    float v = 0.f;
+    if (m < H && n < H) v = __ldg(frame + (size_t)m * H + n);
+    Xs[i] = v;
+    part += v;
+  }
+  // The frame mean only feeds C[0][0], which every band mask zeroes; removing it up front keeps
+  // the fp32 accumulations small (better agreement with the fp64 truth).
+  const float mean = block_sum(part, red) / (float)(H * H);
+  for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+    const int m = i / Hp, n = i - m * Hp;
+    if (m < H && n < H) Xs[i] -= mean;
+  }
+  __syncthreads();
+  // R1[n][k] = sum_m X[m][n] dct[m][k]
+  {
+    const int tn = Kp >> 2, tiles = (Hp >> 2) * tn;
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+      const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
+      float acc[4][4];
+      zero(acc);
+      tile4x4<false, true, false>(Xs + i0, Hp, nullptr, 0, P.dct_t + j0, Kp, Hp, acc);
+      store_rows(R1 + (size_t)i0 * Kp + j0, Kp, acc);
+    }
+  }
+  __syncthreads();
+  // Ct[l][k] = sum_n dct[n][l] R1[n][k]
+  {
+    const int tn = Kp >> 2, tiles = tn * tn;
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+      const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
+      float acc[4][4];
+      zero(acc);
+      tile4x4<true, false, false>(P.dct_t + i0, Kp, nullptr, 0, R1 + j0, Kp, Hp, acc);
+      store_rows(Ct + (size_t)i0 * Kp + j0, Kp, acc);
+    }
+  }
+  __syncthreads();
+}
+
+// Inner products of one chunk of (band,ch) units: U_u[half*hp + k][x].
+__device__ void band_inner(const PlanDev& P, const LevelDev& L, const float* Ct, float* W, int unit0,
+                           int n_units) {
+  const int hp = L.hp, cp = L.cp;
+  const int tk = hp >> 2, tx = cp >> 2;
+  const int per_job = tk * tx, tiles = n_units * 2 * per_job;
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const int job = t / per_job, r = t - job * per_job;
+    const int u = job >> 1, half = job & 1;
+    const int unit = unit0 + u, b = unit >> 1, ch = unit & 1;
+    const int i0 = (r / tx) << 2, j0 = (r % tx) << 2;       // i: k, j: x
+    const float* mask = L.masks + ((size_t)((b * 2 + ch) * 2 + half) * hp) * hp;
+    const float* tab = L.trig + (size_t)L.inner_sel[ch][half] * hp * cp;
+    float acc[4][4];
+    zero(acc);
+    tile4x4<false, true, true>(Ct + i0, P.Kp, mask + i0, hp, tab + j0, cp, hp, acc);
+    store_rows(W + ((size_t)u * 2 * hp + half * hp + i0) * cp + j0, cp, acc);
+  }
+}
+
+template <class Sink>
+__device__ void band_outer(const LevelDev& L, const float* W, int unit0, int n_units, Sink sink) {
+  const int hp = L.hp, cp = L.cp;
+  const int ty = cp >> 2;
+  const int per_job = ty * ty, tiles = n_units * per_job;
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const int u = t / per_job, r = t - u * per_job;
+    const int i0 = (r / ty) << 2, j0 = (r % ty) << 2;       // i: y, j: x
+    float acc[4][4];
+    zero(acc);
+    tile4x4<true, false, false>(L.trig + i0, cp, nullptr, 0, W + (size_t)u * 2 * hp * cp + j0, cp, 2 * hp, acc);
+    sink(unit0 + u, i0, j0, acc);
+  }
+}
+
+__global__ void __launch_bounds__(kPyrThreads)
+pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T,
+                 const __grid_constant__ OutPtrs outs) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red[32];
+  float* Ct = smem;
+  float* W = smem + P.Kp * P.Kp;
+  const long long n = blockIdx.x;
+  const long long w = n / T;
+  const int t = (int)(n - w * T);
+  frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
+  for (int li = 0; li < P.n_levels; ++li) {
+    const LevelDev& L = P.lv[li];
+    const int total = P.nb * 2;
+    float* out = outs.p[li];
+    const int c = L.c;
+    for (int unit0 = 0; unit0 < total; unit0 += L.units_per_chunk) {
+      const int n_units = min(L.units_per_chunk, total - unit0);
+      band_inner(P, L, Ct, W, unit0, n_units);
+      __syncthreads();
+      band_outer(L, W, unit0, n_units, [&](int unit, int y0, int x0, const float (&acc)[4][4]) {
+        const int b = unit >> 1, ch = unit & 1;
+        float* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c * 2 + ch;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int y = y0 + r;
+          if (y >= c) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int x = x0 + q;
+            if (x < c) base[((size_t)y * c + x) * 2] = acc[r][q];
+          }
+        }
+      });
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace mimamo
+
+using namespace mimamo;
+
+struct mimamo_pyr_plan {
+  PlanDev d;
+  size_t smem_bytes;
+  float* dev_blob;      // one allocation holding every table
+};
+
+extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t nbands,
+                                      const float* dct_t_host, int32_t n_levels,
+                                      const mimamo_pyr_level_desc* levels, mimamo_pyr_plan** plan_out) {
+  MM_REQUIRE(plan_out && dct_t_host && levels, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(n_levels >= 1 && n_levels <= MIMAMO_MAX_LEVELS, MIMAMO_E_VALUE, "n_levels must be in [1,%d]", MIMAMO_MAX_LEVELS);
+  MM_REQUIRE(H >= 1 && Hp % 4 == 0 && Kp % 4 == 0 && Hp >= H && nbands >= 2, MIMAMO_E_VALUE, "bad plan geometry");
+  size_t total = (size_t)Hp * Kp;
+  for (int i = 0; i < n_levels; ++i) {
+    const mimamo_pyr_level_desc& L = levels[i];
+    MM_REQUIRE(L.hp % 4 == 0 && L.cp % 4 == 0 && L.hp >= L.h && L.cp >= L.c && L.hp <= Kp, MIMAMO_E_VALUE, "bad level %d geometry", i);
+    total += (size_t)2 * L.hp * L.cp + (size_t)nbands * 4 * L.hp * L.hp;
+  }
+  mimamo_pyr_plan* plan = new mimamo_pyr_plan();
+  PlanDev& d = plan->d;
+  d.H = H; d.Hp = Hp; d.Kp = Kp; d.nb = nbands; d.n_levels = n_levels;
+  if (cudaMalloc((void**)&plan->dev_blob, total * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc of %zu table bytes failed", total * sizeof(float));
+    delete plan;
+    return MIMAMO_E_CUDA;
+  }
+  float* cur = plan->dev_blob;
+  auto put = [&](const float* host, size_t count) -> const float* {
+    cudaMemcpy(cur, host, count * sizeof(float), cudaMemcpyHostToDevice);
+    const float* at = cur;
+    cur += count;
+    return at;
+  };
+  d.dct_t = put(dct_t_host, (size_t)Hp * Kp);
+  // shared-memory budget: Ct + a work region that must hold the forward scratch (X + R1) and at
+  // least one (band,ch) unit of every level; larger regions batch more units per barrier.
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t ct_floats = (size_t)Kp * Kp;
+  size_t need = (size_t)Hp * Hp + (size_t)Hp * Kp;
+  size_t want = need;
+  for (int i = 0; i < n_levels; ++i) {
+    const size_t unit = (size_t)2 * levels[i].hp * levels[i].cp;
+    need = need > unit ? need : unit;
+    const size_t all = unit * 2 * nbands;
+    want = want > all ? want : all;
+  }
+  const size_t budget_floats = ((size_t)max_optin - 1024) / sizeof(float);
+  if (ct_floats + need > budget_floats) {
+    set_error("frame size %d needs %zu bytes of shared memory per CTA (limit %d): unsupported by the "
+              "shared-memory-resident pyramid kernel", H, (ct_floats + need) * 4, max_optin);
+    cudaFree(plan->dev_blob);
+    delete plan;
+    return MIMAMO_E_RUNTIME;
+  }
+  // Work-region size: big enough to batch every (band,ch) unit of a level between barriers if
+  // that still leaves room for two CTAs per SM; otherwise as large as one CTA may have.
+  const size_t half_budget = budget_floats / 2;
+  size_t work;
+  if (ct_floats + want <= half_budget) work = want;
+  else if (ct_floats + need <= half_budget) work = half_budget - ct_floats;
+  else if (ct_floats + want <= budget_floats) work = want;
+  else work = budget_floats - ct_floats;
+  work &= ~(size_t)3;
+  d.work_floats = (int)work;
+  for (int i = 0; i < n_levels; ++i) {
+    const mimamo_pyr_level_desc& L = levels[i];
+    LevelDev& o = d.lv[i];
+    o.c = L.c; o.h = L.h; o.hp = L.hp; o.cp = L.cp;
+    o.trig = put(L.trig_host, (size_t)2 * L.hp * L.cp);
+    o.masks = put(L.masks_host, (size_t)nbands * 4 * L.hp * L.hp);
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) o.inner_sel[a][b] = L.inner_sel_host[a * 2 + b];
+    const size_t unit = (size_t)2 * L.hp * L.cp;
+    int fit = (int)(work / unit);
+    if (fit > 2 * nbands) fit = 2 * nbands;
+    o.units_per_chunk = fit < 1 ? 1 : fit;
+  }
+  plan->smem_bytes = (ct_floats + work) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(pyr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("pyramid plan setup failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+    cudaFree(plan->dev_blob);
+    delete plan;
+    return MIMAMO_E_CUDA;
+  }
+  *plan_out = plan;
+  return MIMAMO_OK;
+}
+
+extern "C" void mimamo_pyr_plan_destroy(mimamo_pyr_plan* plan) {
+  if (!plan) return;
+  cudaFree(plan->dev_blob);
+  delete plan;
+}
+
+extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows,
+                                int32_t T, float* const* coeff_out, void* stream) {
+  MM_REQUIRE(plan && frames && coeff_out, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(n_windows >= 0 && T >= 1, MIMAMO_E_VALUE, "bad batch geometry");
+  if (n_windows == 0) return MIMAMO_OK;
+  MM_REQUIRE(n_windows * T < (1ll << 31), MIMAMO_E_VALUE, "too many frames for one launch");
+  OutPtrs outs;
+  for (int i = 0; i < plan->d.n_levels; ++i) {
+    MM_REQUIRE(coeff_out[i], MIMAMO_E_VALUE, "null output for level %d", i);
+    outs.p[i] = coeff_out[i];
+  }
+  pyr_build_kernel<<<(unsigned)(n_windows * T), kPyrThreads, plan->smem_bytes, (cudaStream_t)stream>>>(
+      plan->d, frames, T, outs);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
+// accessors used by the fused path in phase_tail.cu
+extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops) {
+  *n_levels = plan->d.n_levels;
+  *nbands = plan->d.nb;
+  for (int i = 0; i < plan->d.n_levels; ++i) crops[i] = plan->d.lv[i].c;
+  return MIMAMO_OK;
+}
