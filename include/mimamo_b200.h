@@ -130,6 +130,11 @@ int  mimamo_head_forward(const mimamo_head* head, const float* phase_0, const fl
                          const float* rgb, int32_t bs, int32_t nf, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (bench.py's roofline leg).
+ * enable=1 resets and starts recording; read after synchronising the stream. */
+int mimamo_profile_gemm(int32_t enable);
+int mimamo_profile_gemm_read(double* total_ms, uint64_t* launches, double* issued_flops);
+
 /* Test hook: one conv layer through the tcgen05 implicit-GEMM engine.
  * x bf16 NHWC [B,H,W,Cin] (Cin multiple of 8), w f32 [Cout,Cin,k,k] (torch layout),
  * scale/shift f32[Cout], optional residual bf16 NHWC of the output shape, out bf16 NHWC. */

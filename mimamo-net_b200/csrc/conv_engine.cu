@@ -62,16 +62,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a pipeline bug (wrong expect_tx byte count, bad descriptor) traps instead of
+// hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -374,6 +384,12 @@ static int num_sms() {
   return n;
 }
 
+// optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg)
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+static double g_prof_flops = 0.0;
+
 template <int BLOCK_N, bool BF16>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -384,8 +400,22 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvPara
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t a0, a1;
+      MM_CUDA(cudaEventCreate(&a0));
+      MM_CUDA(cudaEventCreate(&a1));
+      g_prof_events.emplace_back(a0, a1);
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
+    MM_CUDA(cudaEventRecord(e0, stream));
+  }
   conv_gemm_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
   MM_LAUNCH_OK();
+  if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
 }
 
@@ -519,6 +549,28 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
 }  // namespace mimamo
 
 using namespace mimamo;
+
+extern "C" int mimamo_profile_gemm(int32_t enable) {
+  g_profile = enable != 0;
+  g_prof_used = 0;
+  g_prof_flops = 0.0;
+  return MIMAMO_OK;
+}
+
+// Sum of the event-timed durations of every GEMM launch since mimamo_profile_gemm(1); the caller
+// must have synchronised the stream.  issued_flops counts the MMA work actually issued (padded tiles).
+extern "C" int mimamo_profile_gemm_read(double* total_ms, uint64_t* launches, double* issued_flops) {
+  double tot = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float ms = 0.f;
+    MM_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = g_prof_used;
+  if (issued_flops) *issued_flops = g_prof_flops;
+  return MIMAMO_OK;
+}
 
 // Test hook (include/mimamo_b200.h): one convolution through the engine, bf16 NHWC in/out.
 extern "C" int mimamo_conv_bf16(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin, const float* w_host,

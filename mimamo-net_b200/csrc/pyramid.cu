@@ -294,7 +294,12 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
     o.units_per_chunk = fit < 1 ? 1 : fit;
   }
   plan->smem_bytes = (ct_floats + work) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(pyr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  static size_t max_smem_set = 0;          // several plans may coexist: only ever raise the limit
+  cudaError_t e = cudaSuccess;
+  if (plan->smem_bytes > max_smem_set) {
+    e = cudaFuncSetAttribute(pyr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (e == cudaSuccess) max_smem_set = plan->smem_bytes;
+  }
   if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     set_error("pyramid plan setup failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
     cudaFree(plan->dev_blob);

@@ -1,0 +1,63 @@
+"""GPU parity: the tcgen05 implicit-GEMM convolution engine (TMA boxes, TMEM accumulators)
+against a plain fp32 convolution of the same bf16-rounded operands."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad, relu, residual
+    (2, 56, 56, 64, 64, 1, 1, 0, 1, False),      # flat GEMM, one K block
+    (2, 56, 56, 64, 256, 1, 1, 0, 0, False),     # BLOCK_N = 256
+    (3, 28, 28, 512, 128, 1, 1, 0, 1, False),    # 8 K blocks, BLOCK_N = 128, M not a tile multiple
+    (2, 56, 56, 64, 64, 3, 1, 1, 1, False),      # 3x3: shifted 4-D boxes, TMA zero fill = padding
+    (2, 28, 28, 128, 128, 3, 1, 1, 1, False),
+    (3, 14, 14, 256, 256, 3, 1, 1, 1, False),
+    (5, 7, 7, 512, 512, 3, 1, 1, 1, False),      # two images per box
+    (2, 56, 56, 256, 128, 1, 2, 0, 1, False),    # strided 1x1 (TMA element strides)
+    (2, 56, 56, 256, 512, 1, 2, 0, 0, False),
+    (2, 48, 48, 64, 64, 3, 2, 1, 1, False),      # PhaseNet stride-2 3x3
+    (3, 12, 12, 256, 256, 3, 2, 1, 1, False),
+    (2, 14, 14, 256, 1024, 1, 1, 0, 1, True),    # residual add + ReLU epilogue
+    (1, 7, 7, 512, 2048, 1, 1, 0, 1, True),
+    (300, 7, 7, 64, 64, 3, 1, 1, 0, False),      # more tiles than SMs: persistent loop + TMEM double buffer
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_conv_engine(cuda, case):
+    import _native
+    B, H, W, Cin, Cout, k, s, p, relu, use_res = case
+    gen = torch.Generator().manual_seed(sum(case[:8]))
+    x = torch.randn(B, H, W, Cin, generator=gen).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) * (2.0 / (Cin * k * k)) ** 0.5).to(torch.bfloat16).float()
+    scale = (1 + 0.1 * torch.randn(Cout, generator=gen)).float()
+    shift = (0.1 * torch.randn(Cout, generator=gen)).float()
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(B, Ho, Wo, Cout, generator=gen).to(torch.bfloat16) if use_res else None
+    xd = x.to(cuda)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+    resd = res.to(cuda) if use_res else None
+    wn, sn, tn = (np.ascontiguousarray(t.numpy()) for t in (w, scale, shift))
+    rc = _native.lib().mimamo_conv_bf16(_native.dptr(xd), B, H, W, Cin, _native.f32_host_ptr(wn), _native.f32_host_ptr(sn),
+                                        _native.f32_host_ptr(tn), Cout, k, s, p, relu,
+                                        _native.dptr(resd) if use_res else None, _native.dptr(out),
+                                        _native.stream_ptr(cuda))
+    _native.check(rc)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2).to(cuda), w.to(cuda), stride=s, padding=p)
+    ref = ref * scale.to(cuda)[None, :, None, None] + shift.to(cuda)[None, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    if use_res:
+        ref = ref + resd.float()
+    if relu:
+        ref = ref.clamp_min(0)
+    got = out.float()
+    assert torch.isfinite(got).all(), "unwritten / non-finite outputs"
+    err = (got - ref).abs()
+    tol = 2e-2 + 1e-2 * ref.abs()                 # bf16 output rounding (2^-8 relative) + fp32 sum order
+    assert (err <= tol).all(), "max err %.4f at ref %.4f" % (err.max().item(), ref.flatten()[err.argmax()].item())

@@ -1,0 +1,131 @@
+"""GPU parity: steerable pyramid + phase tail through the C ABI vs the reference's outputs
+(tests/golden, written by the unmodified reference) and vs the oracle.
+
+Tolerances (BASELINE.json north_star): phase maps within 1e-4 abs (fp32).  The reference's own
+fp32 arithmetic sits 2e-5..1e-4 from the fp64 truth, so the fp64 distance
+is checked as well.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mimamo_oracle as O
+
+pytestmark = pytest.mark.gpu
+PHASE_TOL = 1e-4
+COEFF_TOL = 2e-6
+
+
+def _pde(height, nbands, levels):
+    from phase_difference_extractor import Phase_Difference_Extractor
+    return Phase_Difference_Extractor(height=height, nbands=nbands, extract_level=levels)
+
+
+def _as_list(x):
+    return x if isinstance(x, list) else [x]
+
+
+@pytest.mark.parametrize("name", ["pde_cfg1", "pde_tester", "pde_odd", "pde_3lvl"])
+def test_against_reference_fixtures(cuda, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = torch.from_numpy(g["x"])
+    levels = [int(l) for l in g["levels"]]
+    pde = _pde(int(g["height"]), int(g["nbands"]), levels)
+    coeffs = _as_list(pde.build_pyramid(x.to(cuda)))
+    fused = _as_list(pde.phase_difference(x.to(cuda)))
+    truth = O.build_pyramid(x.double(), int(g["height"]), int(g["nbands"]), levels, dtype=torch.float64)
+    for i, (c, f) in enumerate(zip(coeffs, fused)):
+        ref_d = torch.from_numpy(g["diff%d" % i])
+        if "coeff%d" % i in g:
+            ref_c = torch.from_numpy(g["coeff%d" % i])
+            assert c.shape == ref_c.shape
+            err_c = (c.cpu() - ref_c).abs().max().item()
+            err_t = (c.cpu().double() - truth[i]).abs().max().item()
+            ref_t = (ref_c.double() - truth[i]).abs().max().item()
+            print("%s level %d: coeff |gpu-ref| %.2e  |gpu-fp64| %.2e  |ref-fp64| %.2e" % (name, i, err_c, err_t, ref_t))
+            assert err_c < COEFF_TOL
+            # the tail alone, fed the reference's own coefficients
+            d = pde.extract(ref_c.to(cuda)).cpu()
+            assert (d - ref_d).abs().max().item() < 2e-5
+        assert f.shape == ref_d.shape
+        err = (f.cpu() - ref_d).abs()
+        truth_d = O.extract(truth[i])
+        err64 = (f.cpu().double() - truth_d).abs().max().item()
+        ref64 = (ref_d.double() - truth_d).abs().max().item()
+        print("%s level %d: phase |gpu-ref| max %.2e, frac>1e-4 %.2e; |gpu-fp64| %.2e, |ref-fp64| %.2e"
+              % (name, i, err.max().item(), (err > PHASE_TOL).float().mean().item(), err64, ref64))
+        assert err.max().item() < PHASE_TOL
+        # unfused path (build_pyramid -> extract) is the same computation
+        assert torch.equal(pde.extract(c), f)
+
+
+def test_tester_shapes_and_channel_order(cuda):
+    """Tester.phase_diff_output layout: channel = band*12 + t (api/tester.py:131-138)."""
+    from tester import Tester
+    x = torch.rand(2, 3, 13, 48, 48, generator=torch.Generator().manual_seed(11))
+    pde = _pde(4, 2, [1, 2])
+    p0, p1 = Tester.phase_diff_output(None, x.to(cuda), pde)
+    assert p0.shape == (2, 3, 24, 48, 48) and p1.shape == (2, 3, 24, 24, 24)
+    r0, r1 = O.phase_diff_output(x)
+    assert (p0.cpu() - r0).abs().max() < PHASE_TOL and (p1.cpu() - r1).abs().max() < PHASE_TOL
+
+
+def test_properties_at_bench_size(cuda):
+    """Full bench-size batch (2048 windows): size-independent properties instead of an oracle run."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(2048, 13, 48, 48, generator=gen).to(cuda)
+    pde = _pde(4, 2, [1, 2])
+    d0, d1 = pde.phase_difference(x)
+    assert d0.shape == (2048, 2, 12, 48, 48) and d1.shape == (2048, 2, 12, 24, 24)
+    for d in (d0, d1):
+        assert torch.isfinite(d).all()
+        assert d.abs().max().item() <= 5 * math.pi + 1e-5                     # clamp
+        clamped = (d.abs() >= 5 * math.pi - 1e-6).flatten(3).any(-1)
+        m = d.flatten(3).mean(-1)
+        assert m[~clamped].abs().max().item() < 1e-4                           # spatial mean removed
+    # windows are independent: a permuted batch gives the permuted result, bit for bit
+    perm = torch.randperm(2048, generator=gen).to(cuda)
+    e0, e1 = pde.phase_difference(x[perm])
+    assert torch.equal(e0, d0[perm]) and torch.equal(e1, d1[perm])
+    # spot-check 4 windows against the oracle
+    idx = [0, 777, 1500, 2047]
+    r0, r1 = [O.extract(c) for c in O.build_pyramid(x[idx].cpu(), 4, 2, [1, 2])]
+    assert (d0[idx].cpu() - r0).abs().max() < PHASE_TOL and (d1[idx].cpu() - r1).abs().max() < PHASE_TOL
+
+
+def test_constant_and_static_inputs(cuda):
+    pde = _pde(4, 2, [1, 2])
+    frame = torch.rand(1, 1, 48, 48, generator=torch.Generator().manual_seed(1))
+    static = frame.expand(1, 13, 48, 48).contiguous().to(cuda)
+    for d in _as_list(pde.phase_difference(static)):
+        assert d.abs().max().item() == 0.0                                     # no motion -> no phase change
+    ref = [O.extract(c) for c in O.build_pyramid(static.cpu(), 4, 2, [1, 2])]
+    assert all(r.abs().max().item() == 0.0 for r in ref)
+
+
+def test_edge_shapes(cuda):
+    pde = _pde(4, 2, [1, 2])
+    empty = pde.phase_difference(torch.zeros(0, 13, 48, 48, device=cuda))
+    assert empty[0].shape == (0, 2, 12, 48, 48) and empty[1].shape == (0, 2, 12, 24, 24)
+    x = torch.rand(3, 2, 48, 48, generator=torch.Generator().manual_seed(2))       # T = 2: a single difference
+    got = pde.phase_difference(x.to(cuda))
+    ref = [O.extract(c) for c in O.build_pyramid(x, 4, 2, [1, 2])]
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and (a.cpu() - b).abs().max() < PHASE_TOL
+    single = _pde(4, 2, 1)                                                         # int extract_level -> tensor
+    c = single.build_pyramid(x.to(cuda))
+    assert torch.is_tensor(c) and c.shape == (3, 2, 2, 48, 48, 2)
+    with pytest.raises(AssertionError):
+        pde.build_pyramid(x)                                                       # CPU tensor: device mismatch
+
+
+def test_tiled_tail_matches_whole_map(cuda):
+    """Maps above 56x56 are split into 32x32 tiles with a two-phase mean; same numbers expected."""
+    x = torch.rand(1, 4, 112, 112, generator=torch.Generator().manual_seed(9))
+    c = O.build_pyramid(x, 4, 4, [1])[0]
+    ref = O.extract(c)
+    got = _pde(4, 4, [1]).extract(c.to(cuda)).cpu()
+    assert (got - ref).abs().max() < 2e-5
