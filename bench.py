@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up, device-timed leg only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -145,7 +146,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    args.warmup = max(args.warmup, 3)
+    if not args.quick:
+        args.warmup = max(args.warmup, 3)
 
     resnet_sd, head_sd = synthetic_weights()
     tester = Tester(None, batch_size=CLIPS, resnet_model=resnet_sd, head_state_dict=head_sd)
@@ -200,9 +202,12 @@ def main():
     gemm_ms, gemm_n, issued = ctypes.c_double(0), ctypes.c_uint64(0), ctypes.c_double(0)
     lib.mimamo_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(gemm_n), ctypes.byref(issued))
     lib.mimamo_profile_gemm(0)
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    if args.quick:
+        e2e_ms = float("nan")
+    else:
+        for _ in range(2):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -232,7 +237,7 @@ def main():
                      "issued_tflops": issued.value / (gemm_ms.value / 1e3) / 1e12 if gemm_ms.value > 0 else None},
         "clocks": sampler.summary(),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         v, stages, cores = cpu_reference_rate()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "64 windows (pyramid+phase, head) + 16 images (ResNet50 fp32), composed per window",

@@ -57,8 +57,9 @@ class Phase_Difference_Extractor(object):
         plan, bs, T, frames = self._prepare(im_batch, symmetry)
         outs = [torch.empty((bs, self.nbands, T, c, c, 2), dtype=torch.float32, device=frames.device)
                 for c in plan.crops]
-        _native.check(_native.lib().mimamo_pyr_build(plan.handle, _native.dptr(frames), bs, T,
-                                                     _native.ptr_array(outs), _native.stream_ptr(frames.device)))
+        if bs * T > 0:
+            _native.check(_native.lib().mimamo_pyr_build(plan.handle, _native.dptr(frames), bs, T,
+                                                         _native.ptr_array(outs), _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
     def extract_coeff_level(self, level, coeff_batch):
@@ -73,6 +74,8 @@ class Phase_Difference_Extractor(object):
         assert coeff_batch.is_cuda and coeff_batch.dtype == torch.float32, 'coefficients must be float32 on the GPU'
         coeff = coeff_batch.contiguous()
         out = torch.empty((bs, n_bands, n_phase_frames - 1, W, H), dtype=torch.float32, device=coeff.device)
+        if out.numel() == 0:
+            return out
         lib = _native.lib()
         need = ctypes.c_size_t(0)
         _native.check(lib.mimamo_phase_extract_workspace_bytes(bs * n_bands, n_phase_frames, W, H, ctypes.byref(need)))
@@ -88,6 +91,8 @@ class Phase_Difference_Extractor(object):
         plan, bs, T, frames = self._prepare(im_batch, True)
         outs = [torch.empty((bs, self.nbands, T - 1, c, c), dtype=torch.float32, device=frames.device)
                 for c in plan.crops]
+        if bs == 0 or T < 2:
+            return outs[0] if isinstance(self.extract_level, int) else outs
         lib = _native.lib()
         need = ctypes.c_size_t(0)
         _native.check(lib.mimamo_pyr_phase_workspace_bytes(plan.handle, bs, T, ctypes.byref(need)))
