@@ -202,6 +202,19 @@ def main():
     gemm_ms, gemm_n, issued = ctypes.c_double(0), ctypes.c_uint64(0), ctypes.c_double(0)
     lib.mimamo_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(gemm_n), ctypes.byref(issued))
     lib.mimamo_profile_gemm(0)
+    # per-stage device time (same inputs, each stage alone), reported next to the whole-step number
+    def stage_ms(fn, reps=3):
+        fn()
+        return timed(fn, reps) / reps
+
+    with torch.no_grad():
+        pde, rn, hd = tester.phase_difference_extractor, tester.resnet50_extractor, tester.model
+        p0, p1 = tester.phase_diff_output(gray_d, pde)
+        feats = rn.features(rgb_d).view(CLIPS, FRAMES, 2048)
+        stages = {"pyramid_phase_ms": stage_ms(lambda: tester.phase_diff_output(gray_d, pde)),
+                  "resnet50_ms": stage_ms(lambda: rn.features(rgb_d)),
+                  "head_ms": stage_ms(lambda: hd([p0, p1], feats))}
+        del p0, p1, feats
     if args.quick:
         e2e_ms = float("nan")
     else:
@@ -235,6 +248,7 @@ def main():
                      "kernel_share_of_step": gemm_ms.value / ms if ms else None,
                      "launches_per_step": gemm_n.value / args.steps,
                      "issued_tflops": issued.value / (gemm_ms.value / 1e3) / 1e12 if gemm_ms.value > 0 else None},
+        "stage_ms": stages,
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:

@@ -27,7 +27,9 @@ namespace mimamo {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                   // 64 x 2 B = one 128-byte swizzle atom
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
-constexpr int kGemmThreads = 192;             // 1 TMA warp + 1 MMA warp + 4 epilogue warps
+constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 1 TMA warp + 1 MMA warp + epilogue warps
+constexpr int kResDepth = 4;                  // residual prefetch ring: chunks (32 columns) in flight per warp
 constexpr int kUmmaK = 16;
 
 struct ConvParams {
@@ -166,25 +168,47 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HAS_RES>
 struct GemmCfg {
   static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int kEpiBytes = kEpiWarps * 32 * 128;                       // TMEM -> coalesced-layout staging
+  static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
+  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
+  static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N;          // double-buffered accumulator (128/256/512)
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 256 + 1024;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
-template <int BLOCK_N, bool BF16>
+// output pixel of accumulator row `row` of M tile `m_tile` (-1: padding row, nothing to store)
+__device__ __forceinline__ int row_pixel(const ConvParams& p, int m_tile, int row) {
+  if (p.mode == 0) {
+    const long long q = (long long)m_tile * kBlockM + row;
+    return q < p.M_total ? (int)q : -1;
+  }
+  const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
+  const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
+  const int per_img = p.bw * p.bh;
+  const int dn = row / per_img, rem = row - dn * per_img;
+  const int dh = rem / p.bw, dw = rem - dh * p.bw;
+  const int n = tn * p.bn + dn, h = th * p.bh + dh, w = tw * p.bw + dw;
+  return (row < p.a_rows && n < p.Nimg && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
+}
+
+template <int BLOCK_N, bool BF16, bool HAS_RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kAStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBStageBytes);
+  uint8_t* sEpi = sB + STAGES * Cfg::kBStageBytes;
+  uint8_t* sRes = sEpi + Cfg::kEpiBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sRes + Cfg::kResBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -195,7 +219,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -267,61 +291,107 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // --------------------------------- epilogue -----------------------------------
+    // TMEM -> registers (thread = output row) -> XOR-swizzled fp32 staging in shared memory ->
+    // (lane = 8 channels of 8 rows) so that every global access is a coalesced 16-byte vector.
+    // The residual is prefetched by per-lane cp.async into a ring kResDepth chunks deep that runs
+    // ahead ACROSS tiles (each lane later consumes exactly the bytes it fetched: no extra sync).
+    const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
-    const int row = quarter * 32 + lane;
+    const int half = ew >> 2;                                 // which half of the tile's columns
+    constexpr int COLS = BLOCK_N / 2;                         // columns per epilogue warp
+    constexpr int CPW = COLS / 32;                            // 32-column chunks per warp per tile
+    const uint32_t stage_u32 = smem_u32(sEpi + ew * (32 * 128));
+    const uint32_t res_u32 = smem_u32(sRes + ew * (kResDepth * 2048));
+    const int sub_row = lane >> 2, pair = lane & 3;           // phase 2: row (it*8 + sub_row), channels pair*8..+8
+    const uint16_t* res_base = reinterpret_cast<const uint16_t*>(p.residual);
+
+    auto issue_residual = [&](int q) {                        // chunk q of this warp's flattened (tile, chunk) list
+      if (HAS_RES) {
+        const int tile = blockIdx.x + (q / CPW) * gridDim.x;
+        if (tile < num_tiles) {
+          const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+          const int ch = n_tile * BLOCK_N + half * COLS + (q % CPW) * 32 + pair * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rp = row_pixel(p, m_tile, quarter * 32 + it * 8 + sub_row);
+            if (rp >= 0) {
+              const uint32_t dst = res_u32 + (q % kResDepth) * 2048 + (it * 32 + lane) * 16;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(res_base + (size_t)rp * p.ld_res + ch) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+    int qc = 0;                                               // chunks consumed so far
+    for (int q = 0; q < kResDepth; ++q) issue_residual(q);
+
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      long long pix = 0;
-      bool valid;
-      if (p.mode == 0) {
-        pix = (long long)m_tile * kBlockM + row;
-        valid = pix < p.M_total;
-      } else {
-        const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
-        const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
-        const int per_img = p.bw * p.bh;
-        const int dn = row / per_img, rem = row - dn * per_img;
-        const int dh = rem / p.bw, dw = rem - dh * p.bw;
-        const int n = tn * p.bn + dn, h = th * p.bh + dh, w = tw * p.bw + dw;
-        valid = row < p.a_rows && n < p.Nimg && h < p.Ho && w < p.Wo;
-        pix = ((long long)n * p.Ho + h) * p.Wo + w;
-      }
-      const int n0 = n_tile * BLOCK_N;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + pix * p.ldc + n0;
-      const uint16_t* rrow = p.residual ? reinterpret_cast<const uint16_t*>(p.residual) + pix * p.ld_res + n0 : nullptr;
+      const int pix = row_pixel(p, m_tile, quarter * 32 + lane);
+      const int n0 = n_tile * BLOCK_N + half * COLS;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
+      for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         tmem_ld_wait();
-        if (valid) {
-          uint32_t packed[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            float a = __uint_as_float(v[j]) * __ldg(p.scale + n0 + c0 + j) + __ldg(p.shift + n0 + c0 + j);
-            float b = __uint_as_float(v[j + 1]) * __ldg(p.scale + n0 + c0 + j + 1) + __ldg(p.shift + n0 + c0 + j + 1);
-            if (rrow) {
-              const float2 r = unpack2<BF16>(*reinterpret_cast<const uint32_t*>(rrow + c0 + j));
-              a += r.x; b += r.y;
-            }
-            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            packed[j >> 1] = pack2<BF16>(a, b);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        for (int g = 0; g < 8; ++g) {                         // 8 chunks of 4 fp32; physical chunk = g ^ (row & 7)
+          const uint32_t addr = stage_u32 + lane * 128 + ((g ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * g]), "r"(v[4 * g + 1]),
+                       "r"(v[4 * g + 2]), "r"(v[4 * g + 3]) : "memory");
         }
+        if (HAS_RES) asm volatile("cp.async.wait_group %0;" ::"n"(kResDepth - 1) : "memory");
+        __syncwarp();
+        const int ch = n0 + c0 + pair * 8;
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + ch + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + ch)), t1 = __ldg(reinterpret_cast<const float4*>(p.shift + ch + 4));
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + sub_row;
+          const int rp = __shfl_sync(0xffffffffu, pix, r);
+          float4 a, b;
+          const uint32_t a0 = stage_u32 + r * 128 + (((2 * pair) ^ (r & 7)) << 4);
+          const uint32_t a1 = stage_u32 + r * 128 + (((2 * pair + 1) ^ (r & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(a0));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(a1));
+          if (rp >= 0) {
+            float o[8] = {a.x * s0.x + t0.x, a.y * s0.y + t0.y, a.z * s0.z + t0.z, a.w * s0.w + t0.w,
+                          b.x * s1.x + t1.x, b.y * s1.y + t1.y, b.z * s1.z + t1.z, b.w * s1.w + t1.w};
+            if (HAS_RES) {
+              uint32_t rw[4];
+              const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + (it * 32 + lane) * 16;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(src));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack2<BF16>(rw[j]);
+                o[2 * j] += f.x; o[2 * j + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            const uint4 pk = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
+                                        pack2<BF16>(o[6], o[7]));
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)rp * p.ldc + ch) = pk;
+          }
+        }
+        __syncwarp();
+        issue_residual(qc + kResDepth);                       // refill the ring slot just consumed
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (HAS_RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -390,12 +460,12 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
 
-template <int BLOCK_N, bool BF16>
+template <int BLOCK_N, bool BF16, bool HAS_RES>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
@@ -413,18 +483,28 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvPara
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
-  conv_gemm_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
+  conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
 }
 
+template <int BLOCK_N>
+static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
+  if (bf) return res ? launch_cfg<BLOCK_N, true, true>(a, b, p, s) : launch_cfg<BLOCK_N, true, false>(a, b, p, s);
+  return res ? launch_cfg<BLOCK_N, false, true>(a, b, p, s) : launch_cfg<BLOCK_N, false, false>(a, b, p, s);
+}
+
+// BLOCK_N actually launched: residual layers use at most 128 columns (the residual ring takes the
+// shared memory of two 256-wide pipeline stages).
+static int effective_block_n(const ConvLayer& L, bool has_res) { return (has_res && L.block_n > 128) ? 128 : L.block_n; }
+
 static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
-  const bool bf = L.elem == kBF16;
-  switch (L.block_n) {
-    case 64:  return bf ? launch_cfg<64, true>(a, b, p, s) : launch_cfg<64, false>(a, b, p, s);
-    case 128: return bf ? launch_cfg<128, true>(a, b, p, s) : launch_cfg<128, false>(a, b, p, s);
-    case 256: return bf ? launch_cfg<256, true>(a, b, p, s) : launch_cfg<256, false>(a, b, p, s);
+  const bool bf = L.elem == kBF16, res = p.residual != nullptr;
+  switch (effective_block_n(L, res)) {
+    case 64:  return launch_n<64>(bf, res, a, b, p, s);
+    case 128: return launch_n<128>(bf, res, a, b, p, s);
+    case 256: return launch_n<256>(bf, res, a, b, p, s);
   }
   set_error("unsupported BLOCK_N %d", L.block_n);
   return MIMAMO_E_RUNTIME;
@@ -460,24 +540,26 @@ void conv_layer_free(ConvLayer& L) {
   L.w_dev = nullptr; L.scale_dev = L.shift_dev = nullptr;
 }
 
-static int weight_map(const ConvLayer& L, CUtensorMap* map) {
+static int weight_map(const ConvLayer& L, CUtensorMap* map, int block_n) {
   const uint64_t K = (uint64_t)L.ksize * L.ksize * L.Cin_p;
   const uint64_t dims[2] = {K, (uint64_t)L.Cout};
   const uint64_t strides[1] = {K * 2};
-  const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)L.block_n};
+  const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
   const uint32_t es[2] = {1, 1};
   return encode_map(map, L.elem, 2, L.w_dev, dims, strides, box, es);
 }
 
-static void fill_common(ConvParams& p, const ConvLayer& L, void* out, int ldc, const void* residual, int ld_res) {
-  p.idesc = make_idesc(L.block_n, L.elem);
+static int fill_common(ConvParams& p, const ConvLayer& L, void* out, int ldc, const void* residual, int ld_res) {
+  const int bn = effective_block_n(L, residual != nullptr);
+  p.idesc = make_idesc(bn, L.elem);
   p.scale = L.scale_dev; p.shift = L.shift_dev;
   p.residual = residual; p.out = out; p.ldc = ldc; p.ld_res = ld_res; p.relu = L.relu;
-  p.n_tiles = L.Cout / L.block_n;
+  p.n_tiles = L.Cout / bn;
   p.cin_blocks = L.Cin_p / kBlockK;
   p.taps_w = L.ksize;
   p.num_k_blocks = L.ksize * L.ksize * p.cin_blocks;
   p.stride = L.stride; p.pad = L.pad;
+  return bn;
 }
 
 int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, const void* residual, int ld_res,
@@ -492,11 +574,10 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   const uint32_t es[2] = {1, 1};
   int rc = encode_map(&ma, L.elem, 2, a, dims, strides, box, es);
   if (rc) return rc;
-  rc = weight_map(L, &mb);
-  if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  fill_common(p, L, out, ldc, residual, ld_res);
+  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, residual, ld_res));
+  if (rc) return rc;
   p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
   return launch(L, ma, mb, p, stream);
@@ -531,11 +612,10 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   const uint32_t es[4] = {1, (uint32_t)L.stride, (uint32_t)L.stride, 1};
   int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
   if (rc) return rc;
-  rc = weight_map(L, &mb);
-  if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  fill_common(p, L, out, ldc, residual, ld_res);
+  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, residual, ld_res));
+  if (rc) return rc;
   p.mode = 1;
   p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
   p.bw = best_bw; p.bh = best_bh; p.bn = best_bn;
@@ -543,6 +623,39 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.tiles_h = (Ho + best_bh - 1) / best_bh;
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
+  return launch(L, ma, mb, p, stream);
+}
+
+// conv1_7x7_s2 without an im2col buffer.  The input is space-to-depth'ed once (2x2 -> 12 (+4 zero)
+// channels, 115x115, padded by 4 original pixels so no coordinate is ever negative); the 7x7/s2
+// convolution becomes a 4x4/s1 one, and the 4 horizontally adjacent s2d pixels of a tap row are
+// 64 contiguous 16-bit values = exactly one 128-byte K block.  The activation tensor map therefore
+// addresses OVERLAPPING windows: dim1 = output column with a 32-byte global stride and a 128-byte
+// extent.  K = 4 rows x 64 = 256 (147 real taps, the rest zero weights).
+int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
+  MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [Cout][256] layer");
+  if (B == 0) return MIMAMO_OK;
+  const int Wo = 112, Ho = 112, S2D = 115;
+  const int bw = 16, bh = 8;
+  CUtensorMap ma, mb;
+  const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)S2D, (uint64_t)B};
+  const uint64_t strides[3] = {32, (uint64_t)S2D * 32, (uint64_t)S2D * S2D * 32};
+  const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  const uint32_t es[4] = {1, 1, 1, 1};
+  int rc = encode_map(&ma, L.elem, 4, s2d, dims, strides, box, es);
+  if (rc) return rc;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, nullptr, 0));
+  if (rc) return rc;
+  p.mode = 1;
+  p.cin_blocks = 1; p.taps_w = 1; p.num_k_blocks = 4;       // K block kb = tap row kb of the 4x4 s2d kernel
+  p.stride = 1; p.pad = 0;
+  p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
+  p.bw = bw; p.bh = bh; p.bn = 1;
+  p.tiles_w = Wo / bw; p.tiles_h = Ho / bh;
+  p.a_rows = bw * bh;
+  p.m_tiles = p.tiles_w * p.tiles_h * B;
   return launch(L, ma, mb, p, stream);
 }
 

@@ -93,6 +93,43 @@ int im2col_conv1(const float* x, int B, void* a, ElemType elem, cudaStream_t s) 
   return MIMAMO_OK;
 }
 
+// ---- conv1 space-to-depth ----------------------------------------------------------------------
+template <bool BF16>
+__global__ void conv1_s2d_kernel(const float* __restrict__ x, long long B, uint4* __restrict__ out) {
+  const long long total = B * 115 * 115;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % 115);
+    const int Y = (int)((i / 115) % 115);
+    const long long b = i / (115 * 115);
+    uint16_t v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int hi = 2 * Y + (q >> 1) - 4, wi = 2 * X + (q & 1) - 4;
+      const bool in = hi >= 0 && hi < 224 && wi >= 0 && wi < 224;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[q * 3 + c] = to16<BF16>(in ? __ldg(x + ((b * 3 + c) * 224 + hi) * 224ll + wi) : 0.f);
+    }
+    v[12] = v[13] = v[14] = v[15] = 0;
+    uint4 o0, o1;
+    o0.x = v[0] | ((uint32_t)v[1] << 16); o0.y = v[2] | ((uint32_t)v[3] << 16);
+    o0.z = v[4] | ((uint32_t)v[5] << 16); o0.w = v[6] | ((uint32_t)v[7] << 16);
+    o1.x = v[8] | ((uint32_t)v[9] << 16); o1.y = v[10] | ((uint32_t)v[11] << 16);
+    o1.z = 0; o1.w = 0;
+    out[i * 2] = o0;
+    out[i * 2 + 1] = o1;
+  }
+}
+
+int conv1_space_to_depth(const float* x, int B, void* s2d, ElemType elem, cudaStream_t s) {
+  if (B == 0) return MIMAMO_OK;
+  const int grid = 148 * 16;
+  if (elem == kBF16) conv1_s2d_kernel<true><<<grid, 256, 0, s>>>(x, B, (uint4*)s2d);
+  else conv1_s2d_kernel<false><<<grid, 256, 0, s>>>(x, B, (uint4*)s2d);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
 // ---- max pool 3x3 s2 ceil_mode --------------------------------------------------------------
 template <bool BF16>
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {

@@ -29,7 +29,9 @@ const int kStageMid[4] = {64, 128, 256, 512};
 
 struct mimamo_resnet50 {
   ElemType elem = kBF16;
-  ConvLayer conv1;                 // 7x7 s2 lowered to a K=147->192 GEMM over an im2col buffer
+  ConvLayer conv1;                 // 7x7 s2 as a 4x4 s1 conv over the space-to-depth'ed input (K = 256)
+  ConvLayer conv1_im2col;          // fallback lowering: K = 147 -> 192 GEMM over an im2col buffer
+  bool use_im2col = false;         // MIMAMO_CONV1=im2col
   std::vector<ResBlock> blocks;
   int chunk = 128;
 };
@@ -50,6 +52,7 @@ static int make_conv(const TensorTable& T, const std::string& name, int cout, in
 extern "C" void mimamo_resnet50_destroy(mimamo_resnet50* net) {
   if (!net) return;
   conv_layer_free(net->conv1);
+  conv_layer_free(net->conv1_im2col);
   for (auto& b : net->blocks) {
     conv_layer_free(b.reduce); conv_layer_free(b.conv3); conv_layer_free(b.increase);
     if (b.has_proj) conv_layer_free(b.proj);
@@ -65,7 +68,25 @@ extern "C" int mimamo_resnet50_create(const mimamo_tensor_desc* tensors, int32_t
   net->elem = (dt && strcmp(dt, "fp16") == 0) ? kF16 : kBF16;
   const char* ck = getenv("MIMAMO_RESNET_CHUNK");
   if (ck && atoi(ck) > 0) net->chunk = atoi(ck);
-  int rc = make_conv(T, "conv1_7x7_s2", 64, 3, 7, 2, 3, 1, net->elem, net->conv1, 147);
+  const char* c1 = getenv("MIMAMO_CONV1");
+  net->use_im2col = c1 && strcmp(c1, "im2col") == 0;
+  int rc = make_conv(T, "conv1_7x7_s2", 64, 3, 7, 2, 3, 1, net->elem, net->conv1_im2col, 147);
+  if (!rc) {
+    // re-pack [64][3][7][7] into the s2d kernel [64][kh'(4)][kw'(4)][(py*2+px)*3+c (16)]
+    const float* w = T.get("conv1_7x7_s2.weight", 64 * 147);
+    std::vector<float> sc, sh, w2((size_t)64 * 256, 0.f);
+    if (!w || !fold_bn(T, "conv1_7x7_s2_bn", 64, 1e-5f, nullptr, sc, sh)) rc = MIMAMO_E_VALUE;
+    for (int o = 0; o < 64 && !rc; ++o)
+      for (int khp = 0; khp < 4; ++khp)
+        for (int kwp = 0; kwp < 4; ++kwp)
+          for (int q = 0; q < 4; ++q) {
+            const int kh = 2 * khp + (q >> 1) - 1, kw = 2 * kwp + (q & 1) - 1;
+            if (kh < 0 || kh > 6 || kw < 0 || kw > 6) continue;
+            for (int c = 0; c < 3; ++c)
+              w2[(size_t)o * 256 + khp * 64 + kwp * 16 + q * 3 + c] = w[((size_t)o * 3 + c) * 49 + kh * 7 + kw];
+          }
+    if (!rc) rc = conv_layer_init(net->conv1, w2.data(), sc.data(), sh.data(), 64, 256, 1, 1, 0, 1, net->elem);
+  }
   int cin = 64;
   for (int s = 0; s < 4 && rc == MIMAMO_OK; ++s) {
     const int mid = kStageMid[s], cout = mid * 4;
@@ -115,8 +136,14 @@ extern "C" int mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x,
   uint16_t* T2 = T1 + (size_t)chunk * 200704;
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = batch - b0 < chunk ? batch - b0 : chunk;
-    int rc = im2col_conv1(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
-    if (!rc) rc = gemm_forward(net->conv1, A0, Bc * 12544, C1, 64, nullptr, 0, stream);
+    int rc;
+    if (net->use_im2col) {
+      rc = im2col_conv1(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
+      if (!rc) rc = gemm_forward(net->conv1_im2col, A0, Bc * 12544, C1, 64, nullptr, 0, stream);
+    } else {
+      rc = conv1_space_to_depth(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
+      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, C1, 64, stream);
+    }
     if (!rc) rc = maxpool3x3s2_ceil(C1, Bc, 112, 112, 64, X, net->elem, stream);
     uint16_t* cur = X;
     uint16_t* nxt = Y;

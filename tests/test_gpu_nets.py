@@ -16,13 +16,14 @@ def _rgb(n, seed):
     return torch.randint(0, 256, (n, 3, 224, 224), generator=g).float() - torch.tensor(O.RESNET_MEAN)[None, :, None, None]
 
 
-@pytest.mark.parametrize("dtype,rel_tol", [("bf16", 4e-2), ("fp16", 6e-3)])
-def test_resnet50_pool5(cuda, dtype, rel_tol, monkeypatch):
+@pytest.mark.parametrize("dtype,rel_tol,conv1", [("bf16", 4e-2, "s2d"), ("fp16", 6e-3, "s2d"), ("bf16", 4e-2, "im2col")])
+def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     """Row R: parity against the restated architecture with seeded synthetic weights (parity with
     the published checkpoint is unpinned: the third-party definition/weights are absent).
     16-bit activations over 53 layers: tolerance is relative to the feature scale."""
     from resnet50_extractor import Resnet50_Extractor
     monkeypatch.setenv("MIMAMO_RESNET_DTYPE", dtype)
+    monkeypatch.setenv("MIMAMO_CONV1", conv1)          # im2col-free (default) vs im2col lowering of conv1
     net = O.resnet_synthetic(1)
     x = _rgb(5, 21)
     ref = O.resnet_pool5(net, x)
