@@ -27,9 +27,9 @@ namespace mimamo {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                   // 64 x 2 B = one 128-byte swizzle atom
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
-constexpr int kEpiWarps = 8;                  // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kEpiWarps = 16;                 // four per TMEM lane quarter, each owning a quarter of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 1 TMA warp + 1 MMA warp + epilogue warps
-constexpr int kResDepth = 4;                  // residual prefetch ring: chunks (32 columns) in flight per warp
+constexpr int kResDepth = 2;                  // residual prefetch ring: chunks (32 columns) in flight per warp
 constexpr int kUmmaK = 16;
 
 struct ConvParams {
@@ -219,7 +219,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -297,9 +297,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ahead ACROSS tiles (each lane later consumes exactly the bytes it fetched: no extra sync).
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
-    const int half = ew >> 2;                                 // which half of the tile's columns
-    constexpr int COLS = BLOCK_N / 2;                         // columns per epilogue warp
+    constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per TMEM quarter (64-wide tiles: 2)
+    const int half = ew >> 2;                                 // which column group this warp owns
+    constexpr int COLS = BLOCK_N / PARTS;                     // columns per epilogue warp
     constexpr int CPW = COLS / 32;                            // 32-column chunks per warp per tile
+    if (half < PARTS) {
     const uint32_t stage_u32 = smem_u32(sEpi + ew * (32 * 128));
     const uint32_t res_u32 = smem_u32(sRes + ew * (kResDepth * 2048));
     const int sub_row = lane >> 2, pair = lane & 3;           // phase 2: row (it*8 + sub_row), channels pair*8..+8
@@ -353,25 +355,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ch = n0 + c0 + pair * 8;
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + ch + 4));
         const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + ch)), t1 = __ldg(reinterpret_cast<const float4*>(p.shift + ch + 4));
+        // all shared-memory reads of the chunk are issued before any is consumed (ILP: the epilogue
+        // is latency-bound, not bandwidth-bound)
+        int rps[4];
+        float4 va[4], vb[4];
+        uint32_t rw[4][4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int r = it * 8 + sub_row;
-          const int rp = __shfl_sync(0xffffffffu, pix, r);
-          float4 a, b;
+          rps[it] = __shfl_sync(0xffffffffu, pix, r);
           const uint32_t a0 = stage_u32 + r * 128 + (((2 * pair) ^ (r & 7)) << 4);
           const uint32_t a1 = stage_u32 + r * 128 + (((2 * pair + 1) ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(a0));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(a1));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va[it].x), "=f"(va[it].y), "=f"(va[it].z), "=f"(va[it].w) : "r"(a0));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb[it].x), "=f"(vb[it].y), "=f"(vb[it].z), "=f"(vb[it].w) : "r"(a1));
+          if (HAS_RES) {
+            const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + (it * 32 + lane) * 16;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[it][0]), "=r"(rw[it][1]), "=r"(rw[it][2]), "=r"(rw[it][3]) : "r"(src));
+          }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rp = rps[it];
+          const float4 a = va[it], b = vb[it];
           if (rp >= 0) {
             float o[8] = {a.x * s0.x + t0.x, a.y * s0.y + t0.y, a.z * s0.z + t0.z, a.w * s0.w + t0.w,
                           b.x * s1.x + t1.x, b.y * s1.y + t1.y, b.z * s1.z + t1.z, b.w * s1.w + t1.w};
             if (HAS_RES) {
-              uint32_t rw[4];
-              const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + (it * 32 + lane) * 16;
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[0]), "=r"(rw[1]), "=r"(rw[2]), "=r"(rw[3]) : "r"(src));
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack2<BF16>(rw[j]);
+                const float2 f = unpack2<BF16>(rw[it][j]);
                 o[2 * j] += f.x; o[2 * j + 1] += f.y;
               }
             }
@@ -392,6 +404,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (HAS_RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -13,6 +13,7 @@
 // 11-tap row pass followed by an 11-tap column pass over zero-padded tiles.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace mimamo {
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ float unwrap_correction(float dd) {
 
 __global__ void __launch_bounds__(kTailThreads)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
-                  const TailGeom g) {
+                  const TailGeom g, const int* __restrict__ root, int nb) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int rin = g.tile_r + 2 * kHalo, cin = g.tile_c + 2 * kHalo;
   const int n_in = rin * cin, n_out = g.tile_r * g.tile_c;
@@ -70,30 +71,53 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
   const bool single = (g.tiles_r * g.tiles_c == 1);
   const int ntiles = g.tiles_r * g.tiles_c;
 
-  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { cum[i] = 0.0; prev[i] = 0.f; }
+  // region cells outside the map are the zero padding of F.conv2d and never change
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) { cum[i] = 0.0; prev[i] = 0.f; mp[i] = 0.f; mg[i] = 0.f; }
+  // clipped rectangle of region cells that lie inside the map
+  const int ry0 = max(0, kHalo - y0), ry1 = min(rin, g.rows + kHalo - y0);
+  const int rx0 = max(0, kHalo - x0), rx1 = min(cin, g.cols + kHalo - x0);
+  const int cw = rx1 - rx0, n_clip = (ry1 - ry0) * cw;
+  // window / band of this map; with de-duplication frame (w,t) reads the coefficients of its root frame
+  const long long win = map / nb;
+  const int band = (int)(map - win * nb);
+  __syncthreads();
 
   for (int t = 0; t < g.T; ++t) {
-    const float2* src = reinterpret_cast<const float2*>(coeff) + ((size_t)map * g.T + t) * plane;
-    // (A) phase, magnitude, unwrap over time
-    for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
-      const int ry = i / cin, rx = i - ry * cin;
-      const int y = y0 - kHalo + ry, x = x0 - kHalo + rx;
-      float vmp = 0.f, vmg = 0.f;                                // zero padding of F.conv2d
-      if (y >= 0 && y < g.rows && x >= 0 && x < g.cols) {
-        const float2 v = __ldg(src + (size_t)y * g.cols + x);
-        const float ph = atan2f(v.y, v.x);
-        const float mag = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+    long long slot = ((size_t)map * g.T + t);
+    if (root != nullptr) {
+      const int r = root[win * g.T + t];
+      slot = ((long long)(r / g.T) * nb + band) * g.T + (r % g.T);
+    }
+    const float2* src = reinterpret_cast<const float2*>(coeff) + (size_t)slot * plane;
+    // (A) phase, magnitude, unwrap over time; loads are issued four at a time for memory-level parallelism
+    for (int i0 = threadIdx.x; i0 < n_clip; i0 += 4 * blockDim.x) {
+      float2 v[4];
+      int cell[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        cell[u] = -1;
+        if (i < n_clip) {
+          const int ry = ry0 + i / cw, rx = rx0 + i % cw;
+          cell[u] = ry * cin + rx;
+          v[u] = __ldg(src + (size_t)(y0 - kHalo + ry) * g.cols + (x0 - kHalo + rx));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = cell[u];
+        if (c < 0) continue;
+        const float ph = atan2f(v[u].y, v[u].x);
+        const float mag = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].x, v[u].x))), 1e-10f);
         float up = ph;
         if (t > 0) {
-          cum[i] += (double)unwrap_correction(__fsub_rn(ph, prev[i]));   // torch CPU cumsum: double acc
-          up = __fadd_rn(ph, (float)cum[i]);
+          cum[c] += (double)unwrap_correction(__fsub_rn(ph, prev[c]));   // torch CPU cumsum: double acc
+          up = __fadd_rn(ph, (float)cum[c]);
         }
-        prev[i] = ph;
-        vmp = __fmul_rn(mag, up);
-        vmg = mag;
+        prev[c] = ph;
+        mp[c] = __fmul_rn(mag, up);
+        mg[c] = mag;
       }
-      mp[i] = vmp;
-      mg[i] = vmg;
     }
     __syncthreads();
     // (B) row pass
@@ -195,7 +219,8 @@ static int tail_setup() {
 }
 
 int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, float* out,
-                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream, const int* root = nullptr,
+                         int nb = 1) {
   MM_REQUIRE(coeff && out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "phase_extract needs T >= 2 frames and a non-empty map");
   if (n_maps == 0) return MIMAMO_OK;
@@ -208,7 +233,7 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   MM_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
-  phase_tail_kernel<<<grid, kTailThreads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g);
+  phase_tail_kernel<<<grid, kTailThreads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
     const long long plane = (long long)rows * cols;
@@ -237,8 +262,56 @@ extern "C" int mimamo_phase_extract(const float* coeff, int64_t n_maps, int32_t 
   return phase_extract_launch(coeff, n_maps, T, rows, cols, out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+// ---- exact frame de-duplication -----------------------------------------------------------------
+// The windows Tester feeds are sliding 13-frame stacks over a clip (api/sampler/snippet_sampler.py:
+// 144-152): window w shares 12 of its 13 frames with window w-1, and clamped windows repeat a
+// frame.  The reference transforms every copy (13x redundant FFT work).
+// Here each frame is compared BITWISE with the two places an identical copy would sit -- slot t-1
+// of its own window and slot t+1 of the previous window -- and the pyramid is built once per
+// distinct frame.  Because the comparison is exact, results are bit-identical to transforming
+// every copy; batches without duplicates just pay for the comparison.
+__global__ void __launch_bounds__(256)
+frame_match_kernel(const uint32_t* __restrict__ frames, int T, int elems, int* __restrict__ parent) {
+  const long long f = blockIdx.x;
+  const long long w = f / T;
+  const int t = (int)(f - w * T);
+  long long cand[2];
+  int nc = 0;
+  if (w > 0 && t < T - 1) cand[nc++] = f - T + 1;
+  if (t > 0) cand[nc++] = f - 1;
+  const uint32_t* a = frames + (size_t)f * elems;
+  long long res = f;
+  for (int c = 0; c < nc; ++c) {
+    const uint32_t* b = frames + (size_t)cand[c] * elems;
+    uint32_t diff = 0;
+    for (int i = threadIdx.x; i < elems; i += blockDim.x) diff |= __ldg(a + i) ^ __ldg(b + i);
+    if (!__syncthreads_or(diff != 0)) { res = cand[c]; break; }
+  }
+  if (threadIdx.x == 0) parent[f] = (int)res;
+}
+
+__global__ void frame_root_kernel(const int* __restrict__ parent, int n, int* __restrict__ root) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  int p = f;
+  while (true) {                       // parents always have a smaller index: terminates at a root
+    const int q = __ldg(parent + p);
+    if (q == p) break;
+    p = q;
+  }
+  root[f] = p;
+}
+
 // ---- P3: frames -> phase-difference maps (Tester.phase_diff_output, api/tester.py:122-139) ----
 extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops);
+
+int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
+                     float* const* coeff_out, const int* root, cudaStream_t stream);
+
+static bool dedup_enabled() {
+  const char* e = getenv("MIMAMO_PYR_DEDUP");
+  return !(e && e[0] == '0');
+}
 
 static int fused_layout(const mimamo_pyr_plan* plan, int64_t n_windows, int T, size_t* coeff_off, size_t* tail_off,
                         size_t* total, int* n_levels, int* nb, int* crops) {
@@ -252,7 +325,7 @@ static int fused_layout(const mimamo_pyr_plan* plan, int64_t n_windows, int T, s
     tail_need = tail_need > b ? tail_need : b;
   }
   *tail_off = cur;
-  *total = cur + align_up(tail_need, 256);
+  *total = cur + align_up(tail_need, 256) + 2 * align_up((size_t)n_windows * T * sizeof(int), 256);   // + parent, root
   return MIMAMO_OK;
 }
 
@@ -274,11 +347,26 @@ extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames
   MM_REQUIRE(workspace && workspace_bytes >= total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", total);
   float* cptr[MIMAMO_MAX_LEVELS];
   for (int i = 0; i < nl; ++i) cptr[i] = reinterpret_cast<float*>((char*)workspace + coff[i]);
-  int rc = mimamo_pyr_build(plan, frames, n_windows, T, cptr, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_frames = n_windows * T;
+  MM_REQUIRE(n_frames < (1ll << 31), MIMAMO_E_VALUE, "too many frames for one call");
+  int* root = nullptr;
+  if (dedup_enabled()) {
+    const size_t idx_bytes = align_up((size_t)n_frames * sizeof(int), 256);
+    int* parent = reinterpret_cast<int*>((char*)workspace + total - 2 * idx_bytes);
+    root = reinterpret_cast<int*>((char*)workspace + total - idx_bytes);
+    int H = 0;
+    mimamo_pyr_plan_levels(plan, &H, nullptr, nullptr);
+    frame_match_kernel<<<(unsigned)n_frames, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(frames), T, H * H, parent);
+    MM_LAUNCH_OK();
+    frame_root_kernel<<<(unsigned)((n_frames + 255) / 256), 256, 0, st>>>(parent, (int)n_frames, root);
+    MM_LAUNCH_OK();
+  }
+  int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, st);
   if (rc) return rc;
   for (int i = 0; i < nl; ++i) {
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
-                              workspace_bytes - toff, (cudaStream_t)stream);
+                              workspace_bytes - toff - 2 * align_up((size_t)n_frames * sizeof(int), 256), st, root, nb);
     if (rc) return rc;
   }
   return MIMAMO_OK;

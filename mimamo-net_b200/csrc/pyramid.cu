@@ -173,12 +173,13 @@ __device__ void band_outer(const LevelDev& L, const float* W, int unit0, int n_u
 
 __global__ void __launch_bounds__(kPyrThreads)
 pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T,
-                 const __grid_constant__ OutPtrs outs) {
+                 const __grid_constant__ OutPtrs outs, const int* __restrict__ root) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
   float* Ct = smem;
   float* W = smem + P.Kp * P.Kp;
   const long long n = blockIdx.x;
+  if (root != nullptr && root[n] != (int)n) return;      // duplicate of an earlier frame: its root's coefficients are reused
   const long long w = n / T;
   const int t = (int)(n - w * T);
   frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
@@ -316,8 +317,8 @@ extern "C" void mimamo_pyr_plan_destroy(mimamo_pyr_plan* plan) {
   delete plan;
 }
 
-extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows,
-                                int32_t T, float* const* coeff_out, void* stream) {
+int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
+                     float* const* coeff_out, const int* root, cudaStream_t stream) {
   MM_REQUIRE(plan && frames && coeff_out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(n_windows >= 0 && T >= 1, MIMAMO_E_VALUE, "bad batch geometry");
   if (n_windows == 0) return MIMAMO_OK;
@@ -327,14 +328,19 @@ extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames
     MM_REQUIRE(coeff_out[i], MIMAMO_E_VALUE, "null output for level %d", i);
     outs.p[i] = coeff_out[i];
   }
-  pyr_build_kernel<<<(unsigned)(n_windows * T), kPyrThreads, plan->smem_bytes, (cudaStream_t)stream>>>(
-      plan->d, frames, T, outs);
+  pyr_build_kernel<<<(unsigned)(n_windows * T), kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root);
   MM_LAUNCH_OK();
   return MIMAMO_OK;
 }
 
+extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows,
+                                int32_t T, float* const* coeff_out, void* stream) {
+  return pyr_build_launch(plan, frames, n_windows, T, coeff_out, nullptr, (cudaStream_t)stream);
+}
+
 // accessors used by the fused path in phase_tail.cu
 extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops) {
+  if (crops == nullptr) { *n_levels = plan->d.H; return MIMAMO_OK; }     // frame size query
   *n_levels = plan->d.n_levels;
   *nbands = plan->d.nb;
   for (int i = 0; i < plan->d.n_levels; ++i) crops[i] = plan->d.lv[i].c;

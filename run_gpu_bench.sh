@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for f in test_gpu_conv test_gpu_nets; do
-  timeout 600 python -m pytest tests/$f.py -q -m gpu -x -s > gpurun_out/$f.log 2>&1; echo "$f exit $?"; tail -3 gpurun_out/$f.log
+for f in test_gpu_conv test_gpu_pyramid test_gpu_nets; do
+  timeout 600 python -m pytest tests/$f.py -q -m gpu -x > gpurun_out/$f.log 2>&1; echo "$f exit $?"; tail -3 gpurun_out/$f.log
 done
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 1500 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 1400 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 200 --csv --log-file gpurun_out/launches_r1.csv python bench.py --quick --steps 1 --warmup 0 > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"

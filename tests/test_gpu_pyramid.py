@@ -129,3 +129,23 @@ def test_tiled_tail_matches_whole_map(cuda):
     ref = O.extract(c)
     got = _pde(4, 4, [1]).extract(c.to(cuda)).cpu()
     assert (got - ref).abs().max() < 2e-5
+
+
+def test_frame_dedup_is_exact(cuda, monkeypatch):
+    """Sliding windows (12 of 13 frames shared with the neighbour, clamped repeats at clip ends):
+    the fused path builds the pyramid once per distinct frame.  Must be bit-identical to
+    transforming every copy, and equal the oracle."""
+    gen = torch.Generator().manual_seed(17)
+    clips = torch.rand(3, 40, 48, 48, generator=gen)
+    clips[1, 5] = clips[1, 4]                                   # a genuine repeated frame inside a clip
+    gray = torch.cat([O.gather_windows(clips[b], 0, 40) for b in range(3)])       # (120, 13, 48, 48)
+    pde = _pde(4, 2, [1, 2])
+    dedup = pde.phase_difference(gray.to(cuda))
+    monkeypatch.setenv("MIMAMO_PYR_DEDUP", "0")
+    plain = pde.phase_difference(gray.to(cuda))
+    for a, b in zip(dedup, plain):
+        assert torch.equal(a, b)
+    idx = [0, 3, 39, 40, 45, 46, 119]
+    ref = [O.extract(c) for c in O.build_pyramid(gray[idx], 4, 2, [1, 2])]
+    for a, r in zip(dedup, ref):
+        assert (a[idx].cpu() - r).abs().max() < PHASE_TOL
