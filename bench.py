@@ -162,13 +162,14 @@ def main():
         return out
 
     def step_e2e():
-        g = gray_h.to(dev, non_blocking=True)
-        r = rgb_h.to(dev, non_blocking=True)
-        out = tester.infer_clips(g, r)
+        # the public host-facing call: pinned host buffers in, host predictions out; the RGB copy is
+        # chunked on a copy stream inside infer_clips_host and overlaps the compute of earlier chunks
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            g = gray_h.to(dev, non_blocking=True)
+            r = rgb_h.to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, tester.infer_clips(g, r))
             return gathered.cpu()
-        return out.cpu()
+        return tester.infer_clips_host(gray_h, rgb_h)
 
     def barrier():
         torch.cuda.synchronize()

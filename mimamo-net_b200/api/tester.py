@@ -124,6 +124,46 @@ class Tester(object):
             return self.model([phase_0, phase_1], feats)
 
 
+    def infer_clips_host(self, gray_windows, rgb_frames, copy_chunk=256):
+        """Same as infer_clips, but from HOST tensors (pinned for true overlap): the RGB batch -- 83 % of
+        the input bytes -- is streamed to the device in chunks on a copy stream, double buffered, while
+        the pyramid and the ResNet50 of earlier chunks run.  Returns a CPU tensor (B, F, 2)."""
+        main = torch.cuda.current_stream(device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device)
+            self._rgb_bufs = [torch.empty((copy_chunk, 3, 224, 224), dtype=torch.float32, device=device) for _ in range(2)]
+        copy, bufs = self._copy_stream, self._rgb_bufs
+        b, f = gray_windows.shape[0], gray_windows.shape[1]
+        n = rgb_frames.shape[0]
+        spans = [(s, min(n, s + copy_chunk)) for s in range(0, n, copy_chunk)]
+        ready = [torch.cuda.Event() for _ in spans]
+        free = [torch.cuda.Event() for _ in spans]
+        copy.wait_stream(main)                                   # buffers may still be in use by an earlier call
+
+        def issue(k):
+            s, e = spans[k]
+            with torch.cuda.stream(copy):
+                if k >= 2:
+                    copy.wait_event(free[k - 2])
+                bufs[k % 2][:e - s].copy_(rgb_frames[s:e], non_blocking=True)
+                ready[k].record(copy)
+
+        with torch.no_grad():
+            for k in range(min(2, len(spans))):
+                issue(k)
+            gray = gray_windows.to(device, non_blocking=True)
+            phase_0, phase_1 = self.phase_diff_output(gray, self.phase_difference_extractor)
+            feats = torch.empty((n, 2048), dtype=torch.float32, device=device)
+            for k, (s, e) in enumerate(spans):
+                main.wait_event(ready[k])
+                feats[s:e] = self.resnet50_extractor.features(bufs[k % 2][:e - s])
+                free[k].record(main)
+                if k + 2 < len(spans):
+                    issue(k + 2)
+            out = self.model([phase_0, phase_1], feats.view(b, f, 2048))
+        return out.cpu()
+
+
 def stitch_predictions(names, ranges, preds):
     """Per-video stitching of snippet predictions (api/tester.py:104-118): later snippets overwrite the
     overlap; asserts full coverage [0, max_len)."""

@@ -101,3 +101,5 @@ def test_end_to_end_clip_path(cuda):
     err = (out - ref).abs().max().item()
     print("end-to-end (bf16 ResNet): valence/arousal max|err| %.3e" % err)
     assert out.shape == (B, Fr, 2) and err < 3e-2
+    host = t.infer_clips_host(gray.pin_memory(), rgb.pin_memory(), copy_chunk=5)     # ragged last chunk
+    assert torch.equal(host, out)
