@@ -1,8 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_nets.py -q -m gpu -x > gpurun_out/test_gpu_nets.log 2>&1; echo "nets exit $?"; tail -3 gpurun_out/test_gpu_nets.log
-for c in 32 64 128 256; do
-  MIMAMO_RESNET_CHUNK=$c timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chunk$c.json 2> gpurun_out/bench.err; echo "chunk $c exit $?"
+for c in 512 1024 2048; do
+  MIMAMO_RESNET_CHUNK=$c timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chunk$c.json 2> gpurun_out/bench.err; echo "chunk $c exit $?"; tail -2 gpurun_out/bench.err
   python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_chunk$c.json'))
