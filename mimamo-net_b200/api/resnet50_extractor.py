@@ -7,7 +7,7 @@ import torch
 import _nets
 from steerable.utils import get_device
 
-device = get_device()
+device = get_device()          # import-time default, like the reference; methods re-query the current device
 
 MEAN = (131.0912, 103.8827, 91.4953)       # resnet50_ferplus_dag meta: 0-255 scale, std 1
 
@@ -59,7 +59,7 @@ class Resnet50_Extractor(object):
     def get_vec(self, image):
         """(bs,3,224,224) -> relu(pool5) as a CPU tensor, like the reference's hook-to-CPU (:74-83),
         including its .squeeze() (bs == 1 collapses the batch dim)."""
-        return self.features(image.to(device)).cpu().squeeze()
+        return self.features(image.to(get_device())).cpu().squeeze()
 
     def run(self, input_dir, output_dir, batch_size=64, video_name=''):
         '''Write one %05d.npy (float32[2048]) per aligned face of <input_dir>/<video>_aligned (:42-73).'''
@@ -75,6 +75,7 @@ class Resnet50_Extractor(object):
         elif len(os.listdir(output_dir)) != 0 and '.npy' in os.listdir(output_dir)[0]:
             print("output_dir {} already exists, feature extraction skipped.".format(output_dir))
             return
+        device = get_device()
         with torch.no_grad():
             for ims, target, img_path, names in loader:
                 feats = self.features(ims.to(device, non_blocking=True)).cpu().numpy()

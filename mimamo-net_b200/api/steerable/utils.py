@@ -3,7 +3,11 @@ The image / visualisation helpers of the reference module are out of scope (SURV
 import torch
 
 
-def get_device(device='cuda:0'):
+def get_device(device=None):
+    """The reference hard-codes 'cuda:0' (api/steerable/utils.py:34); with one process per GPU the
+    default here is the process's CURRENT device (cuda:0 unless torch.cuda.set_device was called)."""
+    if device is None:
+        device = 'cuda:%d' % torch.cuda.current_device() if torch.cuda.device_count() > 0 else 'cuda:0'
     assert isinstance(device, str)
     if 'cuda' in device:
         if torch.cuda.device_count() > 0:

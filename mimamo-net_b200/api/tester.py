@@ -14,7 +14,7 @@ from phase_difference_extractor import Phase_Difference_Extractor
 from mimamo_net import Two_Stream_RNN
 from steerable.utils import get_device
 
-device = get_device()
+device = get_device()          # import-time default, like the reference; methods re-query the current device
 
 
 class Tester(object):
@@ -58,7 +58,7 @@ class Tester(object):
             print("load checkpoint from {}, epoch:{}".format(model_path, checkpoint['epoch']))
         else:
             self.model.load_state_dict(head_state_dict)
-        self.model.to(device)
+        self.model.to(get_device())
         self.model.eval()
         self.label_name = ['valence', 'arousal']
 
@@ -82,6 +82,7 @@ class Tester(object):
     def test_on_dataloader(self, dataloader, model, train_mean=None, train_std=None):
         import pandas as pd
         model.eval()
+        device = get_device()
         names, preds, ranges = [], [], []
         for phase_f, rgb_f, label, rng, name in dataloader:
             with torch.no_grad():
@@ -128,6 +129,7 @@ class Tester(object):
         """Same as infer_clips, but from HOST tensors (pinned for true overlap): the RGB batch -- 83 % of
         the input bytes -- is streamed to the device in chunks on a copy stream, double buffered, while
         the pyramid and the ResNet50 of earlier chunks run.  Returns a CPU tensor (B, F, 2)."""
+        device = get_device()
         main = torch.cuda.current_stream(device)
         if getattr(self, '_copy_stream', None) is None:
             self._copy_stream = torch.cuda.Stream(device)

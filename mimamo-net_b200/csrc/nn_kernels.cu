@@ -292,47 +292,64 @@ int linear_forward(const LinearLayer& L, const float* a, int lda, int M, float* 
 // (SURVEY.md section 0.2).  One CTA owns kGruRows batch rows of one direction for the whole
 // sequence (persistent over time); thread j owns hidden unit j.  Gate order r, z, n as in torch.
 constexpr int kGruRows = 4;
+constexpr int kGruHd = 128, kGruG = 3 * kGruHd;
+constexpr int kGruSmem = (kGruHd * kGruG + 2 * kGruRows * kGruHd + kGruRows * kGruG) * (int)sizeof(float);
 
-__global__ void __launch_bounds__(128)
+// W_hh^T of the CTA's direction (128 x 384 fp32 = 192 KB) is loaded into shared memory once and stays
+// there for the whole sequence; thread g owns gate column g (coalesced, conflict-free reads of W),
+// the hidden state is broadcast from shared memory four k at a time.
+__global__ void __launch_bounds__(kGruG)
 gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, const float* __restrict__ bhh, int S, int Bt,
            float* __restrict__ y) {
-  constexpr int Hd = 128, G = 3 * Hd;
-  __shared__ float h[2][kGruRows][Hd];
-  const int dir = blockIdx.y, j = threadIdx.x;
-  const int row0 = blockIdx.x * kGruRows;
-  const float* W = whhT + (size_t)dir * Hd * G;
-  const float br = bhh[dir * G + j], bz = bhh[dir * G + Hd + j], bn = bhh[dir * G + 2 * Hd + j];
-  for (int r = 0; r < kGruRows; ++r) h[0][r][j] = 0.f;
+  constexpr int Hd = kGruHd, G = kGruG, R = kGruRows;
+  extern __shared__ __align__(16) float gsm[];
+  float* W = gsm;                          // [Hd][G]
+  float* h = W + Hd * G;                   // [2][R][Hd]
+  float* gh = h + 2 * R * Hd;              // [R][G]  W_hh h + b_hh
+  const int dir = blockIdx.y, g = threadIdx.x;
+  const int row0 = blockIdx.x * R;
+  {
+    const float4* src = reinterpret_cast<const float4*>(whhT + (size_t)dir * Hd * G);
+    float4* dst = reinterpret_cast<float4*>(W);
+    for (int i = threadIdx.x; i < Hd * G / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  const float bias = bhh[dir * G + g];
+  for (int i = threadIdx.x; i < R * Hd; i += blockDim.x) h[i] = 0.f;
   __syncthreads();
   int cur = 0;
   for (int step = 0; step < S; ++step) {
     const int s = dir == 0 ? step : S - 1 - step;
-    float ar[kGruRows], az[kGruRows], an[kGruRows];
+    float acc[R];
 #pragma unroll
-    for (int r = 0; r < kGruRows; ++r) { ar[r] = br; az[r] = bz; an[r] = bn; }
-#pragma unroll 4
-    for (int k = 0; k < Hd; ++k) {
-      const float wr = __ldg(W + (size_t)k * G + j), wz = __ldg(W + (size_t)k * G + Hd + j), wn = __ldg(W + (size_t)k * G + 2 * Hd + j);
+    for (int r = 0; r < R; ++r) acc[r] = bias;
+    const float* hc = h + cur * R * Hd;
+#pragma unroll 2
+    for (int k = 0; k < Hd; k += 4) {
+      const float w0 = W[(k + 0) * G + g], w1 = W[(k + 1) * G + g], w2 = W[(k + 2) * G + g], w3 = W[(k + 3) * G + g];
 #pragma unroll
-      for (int r = 0; r < kGruRows; ++r) {
-        const float hv = h[cur][r][k];
-        ar[r] = fmaf(hv, wr, ar[r]); az[r] = fmaf(hv, wz, az[r]); an[r] = fmaf(hv, wn, an[r]);
+      for (int r = 0; r < R; ++r) {
+        const float4 hv = *reinterpret_cast<const float4*>(hc + r * Hd + k);
+        acc[r] = fmaf(hv.x, w0, acc[r]); acc[r] = fmaf(hv.y, w1, acc[r]);
+        acc[r] = fmaf(hv.z, w2, acc[r]); acc[r] = fmaf(hv.w, w3, acc[r]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < kGruRows; ++r) {
+    for (int r = 0; r < R; ++r) gh[r * G + g] = acc[r];
+    __syncthreads();
+    float* hn_buf = h + (cur ^ 1) * R * Hd;
+    for (int i = threadIdx.x; i < R * Hd; i += blockDim.x) {
+      const int r = i / Hd, j = i - r * Hd;
       const int row = row0 + r;
+      float hn = 0.f;
       if (row < Bt) {
         const float* xp = xproj + (((size_t)s * Bt + row) * 2 + dir) * G;
-        const float rg = 1.f / (1.f + expf(-(xp[j] + ar[r])));
-        const float zg = 1.f / (1.f + expf(-(xp[Hd + j] + az[r])));
-        const float ng = tanhf(xp[2 * Hd + j] + rg * an[r]);
-        const float hn = (1.f - zg) * ng + zg * h[cur][r][j];
-        h[cur ^ 1][r][j] = hn;
+        const float rg = 1.f / (1.f + expf(-(xp[j] + gh[r * G + j])));
+        const float zg = 1.f / (1.f + expf(-(xp[Hd + j] + gh[r * G + Hd + j])));
+        const float ng = tanhf(xp[2 * Hd + j] + rg * gh[r * G + 2 * Hd + j]);
+        hn = (1.f - zg) * ng + zg * hc[r * Hd + j];
         y[((size_t)s * Bt + row) * (2 * Hd) + dir * Hd + j] = hn;
-      } else {
-        h[cur ^ 1][r][j] = 0.f;
       }
+      hn_buf[i] = hn;
     }
     __syncthreads();
     cur ^= 1;
@@ -340,10 +357,15 @@ gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, cons
 }
 
 int gru_layer(const float* xproj, const float* whhT, const float* bhh, int S, int Bt, int Hd, float* y, cudaStream_t s) {
-  MM_REQUIRE(Hd == 128, MIMAMO_E_RUNTIME, "GRU kernel is specialised for hidden size 128");
+  MM_REQUIRE(Hd == kGruHd, MIMAMO_E_RUNTIME, "GRU kernel is specialised for hidden size 128");
   if (S == 0 || Bt == 0) return MIMAMO_OK;
+  static bool attr = false;
+  if (!attr) {
+    MM_CUDA(cudaFuncSetAttribute(gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
+    attr = true;
+  }
   dim3 grid((Bt + kGruRows - 1) / kGruRows, 2);
-  gru_kernel<<<grid, 128, 0, s>>>(xproj, whhT, bhh, S, Bt, y);
+  gru_kernel<<<grid, kGruG, kGruSmem, s>>>(xproj, whhT, bhh, S, Bt, y);
   MM_LAUNCH_OK();
   return MIMAMO_OK;
 }

@@ -17,7 +17,7 @@
 
 namespace mimamo {
 
-constexpr int kTailThreads = 256;
+constexpr int kTailThreads = 512;
 constexpr int kHalo = 5;          // (11 - 1) / 2
 constexpr int kTaps = 11;
 constexpr int kWholeMapMax = 56;  // maps up to 56x56 are handled by a single CTA
@@ -25,9 +25,13 @@ constexpr int kTile = 32;
 
 __constant__ float c_gauss[kTaps];
 
+// Tile geometry.  trp/tcp = tile rows/cols rounded up to 4 (the blur passes produce 4 outputs per
+// thread); the input region is (trp + 10) x cin with cin = tcp + 12 so that every row of it starts
+// 16-byte aligned and a thread's four float4 loads stay inside the row.
 struct TailGeom {
   int T, rows, cols;
   int tile_r, tile_c, tiles_r, tiles_c;
+  int trp, tcp, rin, cin;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -50,16 +54,16 @@ __global__ void __launch_bounds__(kTailThreads)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
                   const TailGeom g, const int* __restrict__ root, int nb) {
   extern __shared__ __align__(16) unsigned char raw[];
-  const int rin = g.tile_r + 2 * kHalo, cin = g.tile_c + 2 * kHalo;
-  const int n_in = rin * cin, n_out = g.tile_r * g.tile_c;
+  const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp;
+  const int n_in = rin * cin, n_out = trp * tcp;
   double* cum = reinterpret_cast<double*>(raw);                 // [n_in] running unwrap correction
   float* prev = reinterpret_cast<float*>(cum + n_in);            // [n_in] previous raw phase
-  float* mp = prev + n_in;                                       // [n_in] mag * unwrapped phase
+  float* mp = prev + n_in;                                       // [n_in] mag * unwrapped phase (zero padded)
   float* mg = mp + n_in;                                         // [n_in] mag
-  float* hmp = mg + n_in;                                        // [rin][tile_c] row-blurred
-  float* hmg = hmp + rin * g.tile_c;
-  float* blur_prev = hmg + rin * g.tile_c;                       // [n_out]
-  float* delta = blur_prev + n_out;                              // [n_out]
+  float* hmp = mg + n_in;                                        // [rin][tcp] row-blurred
+  float* hmg = hmp + rin * tcp;
+  float* blur_prev = hmg + rin * tcp;                            // [trp][tcp]
+  float* delta = blur_prev + n_out;                              // [trp][tcp]
   __shared__ double red[kTailThreads / 32];
   __shared__ float mean_s;
 
@@ -73,13 +77,17 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
 
   // region cells outside the map are the zero padding of F.conv2d and never change
   for (int i = threadIdx.x; i < n_in; i += blockDim.x) { cum[i] = 0.0; prev[i] = 0.f; mp[i] = 0.f; mg[i] = 0.f; }
-  // clipped rectangle of region cells that lie inside the map
-  const int ry0 = max(0, kHalo - y0), ry1 = min(rin, g.rows + kHalo - y0);
-  const int rx0 = max(0, kHalo - x0), rx1 = min(cin, g.cols + kHalo - x0);
+  // clipped rectangle of region cells that lie inside the map (region cell (ry,rx) = map pixel
+  // (y0 - 5 + ry, x0 - 5 + rx))
+  const int ry0 = max(0, kHalo - y0), ry1 = min(g.tile_r + 2 * kHalo, g.rows + kHalo - y0);
+  const int rx0 = max(0, kHalo - x0), rx1 = min(g.tile_c + 2 * kHalo, g.cols + kHalo - x0);
   const int cw = rx1 - rx0, n_clip = (ry1 - ry0) * cw;
   // window / band of this map; with de-duplication frame (w,t) reads the coefficients of its root frame
   const long long win = map / nb;
   const int band = (int)(map - win * nb);
+  float gk[kTaps];
+#pragma unroll
+  for (int d = 0; d < kTaps; ++d) gk[d] = c_gauss[d];
   __syncthreads();
 
   for (int t = 0; t < g.T; ++t) {
@@ -120,35 +128,60 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       }
     }
     __syncthreads();
-    // (B) row pass
-    for (int i = threadIdx.x; i < rin * g.tile_c; i += blockDim.x) {
-      const int ry = i / g.tile_c, x = i - ry * g.tile_c;
-      const float* a = mp + ry * cin + x;
-      const float* b = mg + ry * cin + x;
-      float sa = 0.f, sb = 0.f;
+    // (B) row pass: each thread produces 4 adjacent outputs of one row from 16 loaded inputs
+    {
+      const int groups = tcp >> 2;
+      for (int i = threadIdx.x; i < rin * groups; i += blockDim.x) {
+        const int ry = i / groups, xg = (i - ry * groups) << 2;
+        const float4* pa = reinterpret_cast<const float4*>(mp + ry * cin + xg);
+        const float4* pb = reinterpret_cast<const float4*>(mg + ry * cin + xg);
+        float a[16], b[16];
 #pragma unroll
-      for (int d = 0; d < kTaps; ++d) { sa = fmaf(c_gauss[d], a[d], sa); sb = fmaf(c_gauss[d], b[d], sb); }
-      hmp[i] = sa;
-      hmg[i] = sb;
+        for (int q = 0; q < 4; ++q) {
+          const float4 va = pa[q], vb = pb[q];
+          a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
+          b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
+        }
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < kTaps; ++d)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) { sa[o] = fmaf(gk[d], a[o + d], sa[o]); sb[o] = fmaf(gk[d], b[o + d], sb[o]); }
+        *reinterpret_cast<float4*>(hmp + ry * tcp + xg) = make_float4(sa[0], sa[1], sa[2], sa[3]);
+        *reinterpret_cast<float4*>(hmg + ry * tcp + xg) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+      }
     }
     __syncthreads();
-    // (C) column pass, ratio, temporal difference
+    // (C) column pass (4 vertically adjacent outputs per thread), ratio, temporal difference
     double part = 0.0;
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
-      const int y = i / g.tile_c, x = i - y * g.tile_c;
-      if (y < th && x < tw) {
-        const float* a = hmp + y * g.tile_c + x;
-        const float* b = hmg + y * g.tile_c + x;
-        float sa = 0.f, sb = 0.f;
+    {
+      const int ygroups = trp >> 2;
+      for (int i = threadIdx.x; i < ygroups * tcp; i += blockDim.x) {
+        const int yg = (i / tcp) << 2, x = i % tcp;
+        float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int d = 0; d < kTaps; ++d) { sa = fmaf(c_gauss[d], a[d * g.tile_c], sa); sb = fmaf(c_gauss[d], b[d * g.tile_c], sb); }
-        const float val = __fdiv_rn(sa, sb);
-        if (t > 0) {
-          const float dl = __fsub_rn(val, blur_prev[i]);
-          delta[i] = dl;
-          part += (double)dl;
+        for (int r = 0; r < 14; ++r) {
+          const float a = hmp[(yg + r) * tcp + x], b = hmg[(yg + r) * tcp + x];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int d = r - o;
+            if (d >= 0 && d < kTaps) { sa[o] = fmaf(gk[d], a, sa[o]); sb[o] = fmaf(gk[d], b, sb[o]); }
+          }
         }
-        blur_prev[i] = val;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int y = yg + o;
+          if (y < th && x < tw) {
+            const float val = __fdiv_rn(sa[o], sb[o]);
+            const int cell = y * tcp + x;
+            if (t > 0) {
+              const float dl = __fsub_rn(val, blur_prev[cell]);
+              delta[cell] = dl;
+              part += (double)dl;
+            }
+            blur_prev[cell] = val;
+          }
+        }
       }
     }
     if (t > 0) {
@@ -165,13 +198,11 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       const float mean = single ? mean_s : 0.f;
       const float lim = 15.7079632679489656f;                    // 5*pi
       float* dst = out + ((size_t)map * (g.T - 1) + (t - 1)) * plane;
-      for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
-        const int y = i / g.tile_c, x = i - y * g.tile_c;
-        if (y < th && x < tw) {
-          float v = delta[i];
-          if (single) v = fminf(fmaxf(__fsub_rn(v, mean), -lim), lim);
-          dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
-        }
+      for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
+        const int y = i / tw, x = i - y * tw;
+        float v = delta[y * tcp + x];
+        if (single) v = fminf(fmaxf(__fsub_rn(v, mean), -lim), lim);
+        dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
       }
     }
     __syncthreads();
@@ -198,13 +229,17 @@ static TailGeom make_geom(int T, int rows, int cols) {
   else { g.tile_r = kTile; g.tile_c = kTile; }
   g.tiles_r = (rows + g.tile_r - 1) / g.tile_r;
   g.tiles_c = (cols + g.tile_c - 1) / g.tile_c;
+  g.trp = (g.tile_r + 3) / 4 * 4;
+  g.tcp = (g.tile_c + 3) / 4 * 4;
+  g.rin = g.trp + 2 * kHalo;
+  g.cin = g.tcp + 12;
   return g;
 }
 
 static size_t tail_smem(const TailGeom& g) {
-  const size_t rin = g.tile_r + 2 * kHalo, cin = g.tile_c + 2 * kHalo;
-  return rin * cin * (sizeof(double) + 3 * sizeof(float)) + 2 * rin * g.tile_c * sizeof(float) +
-         2 * (size_t)g.tile_r * g.tile_c * sizeof(float);
+  const size_t n_in = (size_t)g.rin * g.cin;
+  return n_in * (sizeof(double) + 3 * sizeof(float)) + 2 * (size_t)g.rin * g.tcp * sizeof(float) +
+         2 * (size_t)g.trp * g.tcp * sizeof(float);
 }
 
 static bool g_tail_ready = false;
@@ -213,7 +248,7 @@ static int tail_setup() {
   float taps[kTaps];
   for (int d = 0; d < kTaps; ++d) taps[d] = (float)exp(-(double)((d - kHalo) * (d - kHalo)) / 8.0);   // std = 2
   MM_CUDA(cudaMemcpyToSymbol(c_gauss, taps, sizeof(taps)));
-  MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
   g_tail_ready = true;
   return MIMAMO_OK;
 }
