@@ -85,6 +85,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 27)) __trap();
   }
 }
+// one lane of a converged warp (warp-uniform control flow keeps loop state in uniform registers,
+// which is what UTMALDG / UTCHMMA take their operands from)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -230,61 +237,101 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------- TMA producer -------------------------------
+      // One lane issues every load, so the per-K-block instruction chain bounds the whole kernel
+      // (measured: ~940 cycles per K-block with integer divisions in the loop).  Everything is
+      // hoisted; the loop body is wait / expect_tx / two TMA issues.  The whole warp runs the loop
+      // (warp-uniform control flow => uniform registers), one elected lane issues.
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes;
+      const int n_tiles = p.n_tiles, mode = p.mode, cin_blocks = p.cin_blocks, taps_w = p.taps_w;
+      const int taps_h = p.num_k_blocks / (cin_blocks * taps_w);
+      const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+      const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
+      const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+      const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+        const int n0 = n_tile * BLOCK_N;
         int c1 = 0, c2 = 0, c3 = 0;
-        if (p.mode == 0) {
+        if (mode == 0) {
           c1 = m_tile * kBlockM;
         } else {
-          const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
-          const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
-          c1 = tw * p.bw * p.stride - p.pad;
-          c2 = th * p.bh * p.stride - p.pad;
-          c3 = tn * p.bn;
+          const int tw = m_tile % tiles_w, rest = m_tile / tiles_w;
+          const int th = rest % tiles_h, tn = rest / tiles_h;
+          c1 = tw * step_w - pad;
+          c2 = th * step_h - pad;
+          c3 = tn * bn;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          if (p.mode == 0) {
-            tma_load_2d(sA + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBlockK, c1);
-          } else {
-            const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
-            tma_load_4d(sA + stage * kAStageBytes, &tmA, &full_bar[stage], cb * kBlockK, c1 + kw, c2 + kh, c3);
+        int kcol = 0;                                          // K offset into the weight matrix
+#pragma unroll 1
+        for (int kh = 0; kh < taps_h; ++kh) {
+#pragma unroll 1
+          for (int kw = 0; kw < taps_w; ++kw) {
+#pragma unroll 1
+            for (int cb = 0; cb < cin_blocks; ++cb, kcol += kBlockK) {
+              const uint32_t fb = full_u32 + stage * 8, eb = empty_u32 + stage * 8;
+              {
+                uint32_t spins = 0;
+                uint32_t ok;
+                do {
+                  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                               : "=r"(ok) : "r"(eb), "r"(phase ^ 1) : "memory");
+                  if (!ok && ++spins > (1u << 27)) __trap();
+                } while (!ok);
+              }
+              const uint32_t dstA = sA_u32 + stage * kAStageBytes, dstB = sB_u32 + stage * Cfg::kBStageBytes;
+              if (elect_one()) {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx_bytes) : "memory");
+              if (mode == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(dstA), "l"(mapA), "r"(fb), "r"(cb * kBlockK), "r"(c1) : "memory");
+              } else {
+                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                             ::"r"(dstA), "l"(mapA), "r"(fb), "r"(cb * kBlockK), "r"(c1 + kw), "r"(c2 + kh), "r"(c3) : "memory");
+              }
+              asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                           ::"r"(dstB), "l"(mapB), "r"(fb), "r"(kcol), "r"(n0) : "memory");
+              }
+              __syncwarp();
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
           }
-          tma_load_2d(sB + stage * Cfg::kBStageBytes, &tmB, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ------------------------------- MMA issuer ---------------------------------
       int stage = 0; uint32_t phase = 0;
       int local = 0;
+      const int nkb = p.num_k_blocks;
+      const uint32_t idesc = p.idesc;
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * kAStageBytes));
-          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * Cfg::kBStageBytes));
+          // stage offsets in the descriptors' (address >> 4) field; +2 per 16-element K step
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kAStageBytes >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (Cfg::kBStageBytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advancing 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the
-            // (address >> 4) field
-            umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
+            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&empty_bar[stage]);                    // frees the smem stage when the MMAs retire
-          if (kb == p.num_k_blocks - 1) umma_commit(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -190,7 +190,7 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       __syncthreads();
       if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int i = 0; i < kTailThreads / 32; ++i) tot += red[i];
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
         if (single) mean_s = (float)(tot / (double)plane);
         else partial[((size_t)map * (g.T - 1) + (t - 1)) * ntiles + tile] = tot;
       }
@@ -268,7 +268,8 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   MM_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
-  phase_tail_kernel<<<grid, kTailThreads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb);
+  const int threads = g.tile_r * g.tile_c >= 1600 ? kTailThreads : (g.tile_r * g.tile_c >= 400 ? 256 : 128);   // small maps: fewer idle threads per barrier
+  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
     const long long plane = (long long)rows * cols;
