@@ -165,9 +165,7 @@ def main():
         # the public host-facing call: pinned host buffers in, host predictions out; the RGB copy is
         # chunked on a copy stream inside infer_clips_host and overlaps the compute of earlier chunks
         if world > 1:
-            g = gray_h.to(dev, non_blocking=True)
-            r = rgb_h.to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, tester.infer_clips(g, r))
+            dist.all_gather_into_tensor(gathered, tester.infer_clips_host(gray_h, rgb_h, to_host=False))
             return gathered.cpu()
         return tester.infer_clips_host(gray_h, rgb_h)
 

@@ -68,9 +68,14 @@ int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t nbands,
 void mimamo_pyr_plan_destroy(mimamo_pyr_plan* plan);
 
 /* frames f32[n_windows*T, H, H]  ->  coeff_out[level] f32[n_windows, nbands, T, c, c, 2]
- * (the layout Phase_Difference_Extractor.build_pyramid returns). */
+ * (the layout Phase_Difference_Extractor.build_pyramid returns).  Frames that fit in shared
+ * memory (H <= ~128) need no workspace; larger frames (e.g. 224x224) run a persistent grid over a
+ * caller-provided scratch. */
+int mimamo_pyr_build_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T,
+                                     size_t* bytes_out);
 int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames,
-                     int64_t n_windows, int32_t T, float* const* coeff_out, void* stream);
+                     int64_t n_windows, int32_t T, float* const* coeff_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * P2: phase tail.  Replaces Phase_Difference_Extractor.extract

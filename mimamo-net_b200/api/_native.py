@@ -38,7 +38,10 @@ _SIGNATURES = {
                                               c_float_p, ctypes.c_int32, ctypes.POINTER(PyrLevelDesc),
                                               ctypes.POINTER(vp)]),
     "mimamo_pyr_plan_destroy": (None, [vp]),
-    "mimamo_pyr_build": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(vp), vp]),
+    "mimamo_pyr_build_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32,
+                                                        ctypes.POINTER(ctypes.c_size_t)]),
+    "mimamo_pyr_build": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(vp), vp,
+                                        ctypes.c_size_t, vp]),
     "mimamo_phase_extract_workspace_bytes": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                             ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_phase_extract": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,

@@ -58,8 +58,12 @@ class Phase_Difference_Extractor(object):
         outs = [torch.empty((bs, self.nbands, T, c, c, 2), dtype=torch.float32, device=frames.device)
                 for c in plan.crops]
         if bs * T > 0:
-            _native.check(_native.lib().mimamo_pyr_build(plan.handle, _native.dptr(frames), bs, T,
-                                                         _native.ptr_array(outs), _native.stream_ptr(frames.device)))
+            lib = _native.lib()
+            need = ctypes.c_size_t(0)
+            _native.check(lib.mimamo_pyr_build_workspace_bytes(plan.handle, bs, T, ctypes.byref(need)))
+            ws = torch.empty((max(need.value, 8),), dtype=torch.uint8, device=frames.device)
+            _native.check(lib.mimamo_pyr_build(plan.handle, _native.dptr(frames), bs, T, _native.ptr_array(outs),
+                                               _native.dptr(ws), ws.numel(), _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
     def extract_coeff_level(self, level, coeff_batch):

@@ -125,10 +125,11 @@ class Tester(object):
             return self.model([phase_0, phase_1], feats)
 
 
-    def infer_clips_host(self, gray_windows, rgb_frames, copy_chunk=256):
+    def infer_clips_host(self, gray_windows, rgb_frames, copy_chunk=256, to_host=True):
         """Same as infer_clips, but from HOST tensors (pinned for true overlap): the RGB batch -- 83 % of
         the input bytes -- is streamed to the device in chunks on a copy stream, double buffered, while
-        the pyramid and the ResNet50 of earlier chunks run.  Returns a CPU tensor (B, F, 2)."""
+        the pyramid and the ResNet50 of earlier chunks run.  Returns a CPU tensor (B, F, 2) (or the device
+        tensor when to_host=False, e.g. to feed a collective)."""
         device = get_device()
         main = torch.cuda.current_stream(device)
         if getattr(self, '_copy_stream', None) is None:
@@ -163,7 +164,7 @@ class Tester(object):
                 if k + 2 < len(spans):
                     issue(k + 2)
             out = self.model([phase_0, phase_1], feats.view(b, f, 2048))
-        return out.cpu()
+        return out.cpu() if to_host else out
 
 
 def stitch_predictions(names, ranges, preds):

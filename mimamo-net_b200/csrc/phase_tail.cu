@@ -342,7 +342,8 @@ __global__ void frame_root_kernel(const int* __restrict__ parent, int n, int* __
 extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops);
 
 int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
-                     float* const* coeff_out, const int* root, cudaStream_t stream);
+                     float* const* coeff_out, const int* root, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+extern "C" int mimamo_pyr_build_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T, size_t* bytes_out);
 
 static bool dedup_enabled() {
   const char* e = getenv("MIMAMO_PYR_DEDUP");
@@ -361,6 +362,9 @@ static int fused_layout(const mimamo_pyr_plan* plan, int64_t n_windows, int T, s
     tail_need = tail_need > b ? tail_need : b;
   }
   *tail_off = cur;
+  size_t pyr_ws = 0;
+  mimamo_pyr_build_workspace_bytes(plan, n_windows, T, &pyr_ws);
+  if (pyr_ws > tail_need) tail_need = pyr_ws;       // the pyramid scratch and the tail partials are never live together
   *total = cur + align_up(tail_need, 256) + 2 * align_up((size_t)n_windows * T * sizeof(int), 256);   // + parent, root
   return MIMAMO_OK;
 }
@@ -398,7 +402,8 @@ extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames
     frame_root_kernel<<<(unsigned)((n_frames + 255) / 256), 256, 0, st>>>(parent, (int)n_frames, root);
     MM_LAUNCH_OK();
   }
-  int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, st);
+  const size_t idx2 = 2 * align_up((size_t)n_frames * sizeof(int), 256);
+  int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, (char*)workspace + toff, total - toff - idx2, st);
   if (rc) return rc;
   for (int i = 0; i < nl; ++i) {
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,

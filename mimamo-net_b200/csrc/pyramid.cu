@@ -30,6 +30,7 @@ struct LevelDev {
 struct PlanDev {
   int H, Hp, Kp, nb, n_levels;
   int work_floats;
+  int large;            // 1: frame too big for shared memory -> spectrum / intermediates live in a per-CTA global scratch
   const float* dct_t;   // [Hp][Kp]
   LevelDev lv[MIMAMO_MAX_LEVELS];
 };
@@ -171,42 +172,47 @@ __device__ void band_outer(const LevelDev& L, const float* W, int unit0, int n_u
   }
 }
 
+template <bool LARGE>
 __global__ void __launch_bounds__(kPyrThreads)
 pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T,
-                 const __grid_constant__ OutPtrs outs, const int* __restrict__ root) {
+                 const __grid_constant__ OutPtrs outs, const int* __restrict__ root, float* scratch, long long n_frames) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
-  float* Ct = smem;
-  float* W = smem + P.Kp * P.Kp;
-  const long long n = blockIdx.x;
-  if (root != nullptr && root[n] != (int)n) return;      // duplicate of an earlier frame: its root's coefficients are reused
-  const long long w = n / T;
-  const int t = (int)(n - w * T);
-  frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
-  for (int li = 0; li < P.n_levels; ++li) {
-    const LevelDev& L = P.lv[li];
-    const int total = P.nb * 2;
-    float* out = outs.p[li];
-    const int c = L.c;
-    for (int unit0 = 0; unit0 < total; unit0 += L.units_per_chunk) {
-      const int n_units = min(L.units_per_chunk, total - unit0);
-      band_inner(P, L, Ct, W, unit0, n_units);
-      __syncthreads();
-      band_outer(L, W, unit0, n_units, [&](int unit, int y0, int x0, const float (&acc)[4][4]) {
-        const int b = unit >> 1, ch = unit & 1;
-        float* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c * 2 + ch;
+  // Small frames: one CTA per frame, everything in shared memory.  Large frames (H > ~128, e.g. the
+  // 224x224 configuration): a persistent grid walks the frames and keeps the same buffers in a
+  // private slice of a caller-provided global scratch (L2-resident), same code otherwise.
+  float* Ct = LARGE ? scratch + (size_t)blockIdx.x * ((size_t)P.Kp * P.Kp + P.work_floats) : smem;
+  float* W = Ct + (size_t)P.Kp * P.Kp;
+  for (long long n = blockIdx.x; n < n_frames; n += gridDim.x) {
+    if (root != nullptr && root[n] != (int)n) continue;    // duplicate of an earlier frame: its root's coefficients are reused
+    const long long w = n / T;
+    const int t = (int)(n - w * T);
+    frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
+    for (int li = 0; li < P.n_levels; ++li) {
+      const LevelDev& L = P.lv[li];
+      const int total = P.nb * 2;
+      float* out = outs.p[li];
+      const int c = L.c;
+      for (int unit0 = 0; unit0 < total; unit0 += L.units_per_chunk) {
+        const int n_units = min(L.units_per_chunk, total - unit0);
+        band_inner(P, L, Ct, W, unit0, n_units);
+        __syncthreads();
+        band_outer(L, W, unit0, n_units, [&](int unit, int y0, int x0, const float (&acc)[4][4]) {
+          const int b = unit >> 1, ch = unit & 1;
+          float* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c * 2 + ch;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int y = y0 + r;
-          if (y >= c) continue;
+          for (int r = 0; r < 4; ++r) {
+            const int y = y0 + r;
+            if (y >= c) continue;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int x = x0 + q;
-            if (x < c) base[((size_t)y * c + x) * 2] = acc[r][q];
+            for (int q = 0; q < 4; ++q) {
+              const int x = x0 + q;
+              if (x < c) base[((size_t)y * c + x) * 2] = acc[r][q];
+            }
           }
-        }
-      });
-      __syncthreads();
+        });
+        __syncthreads();
+      }
     }
   }
 }
@@ -218,6 +224,7 @@ using namespace mimamo;
 struct mimamo_pyr_plan {
   PlanDev d;
   size_t smem_bytes;
+  int large_grid;       // persistent grid size in large-frame mode
   float* dev_blob;      // one allocation holding every table
 };
 
@@ -264,22 +271,20 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
     want = want > all ? want : all;
   }
   const size_t budget_floats = ((size_t)max_optin - 1024) / sizeof(float);
-  if (ct_floats + need > budget_floats) {
-    set_error("frame size %d needs %zu bytes of shared memory per CTA (limit %d): unsupported by the "
-              "shared-memory-resident pyramid kernel", H, (ct_floats + need) * 4, max_optin);
-    cudaFree(plan->dev_blob);
-    delete plan;
-    return MIMAMO_E_RUNTIME;
-  }
-  // Work-region size: big enough to batch every (band,ch) unit of a level between barriers if
-  // that still leaves room for two CTAs per SM; otherwise as large as one CTA may have.
-  const size_t half_budget = budget_floats / 2;
   size_t work;
-  if (ct_floats + want <= half_budget) work = want;
-  else if (ct_floats + need <= half_budget) work = half_budget - ct_floats;
-  else if (ct_floats + want <= budget_floats) work = want;
-  else work = budget_floats - ct_floats;
-  work &= ~(size_t)3;
+  d.large = (ct_floats + need > budget_floats) ? 1 : 0;
+  if (d.large) {
+    work = need;                       // one (band,ch) unit at a time, buffers in global scratch
+  } else {
+    // Work-region size: big enough to batch every (band,ch) unit of a level between barriers if
+    // that still leaves room for two CTAs per SM; otherwise as large as one CTA may have.
+    const size_t half_budget = budget_floats / 2;
+    if (ct_floats + want <= half_budget) work = want;
+    else if (ct_floats + need <= half_budget) work = half_budget - ct_floats;
+    else if (ct_floats + want <= budget_floats) work = want;
+    else work = budget_floats - ct_floats;
+    work &= ~(size_t)3;
+  }
   d.work_floats = (int)work;
   for (int i = 0; i < n_levels; ++i) {
     const mimamo_pyr_level_desc& L = levels[i];
@@ -294,11 +299,14 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
     if (fit > 2 * nbands) fit = 2 * nbands;
     o.units_per_chunk = fit < 1 ? 1 : fit;
   }
-  plan->smem_bytes = (ct_floats + work) * sizeof(float);
+  plan->smem_bytes = d.large ? 0 : (ct_floats + work) * sizeof(float);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  plan->large_grid = 2 * sms;
   static size_t max_smem_set = 0;          // several plans may coexist: only ever raise the limit
   cudaError_t e = cudaSuccess;
   if (plan->smem_bytes > max_smem_set) {
-    e = cudaFuncSetAttribute(pyr_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    e = cudaFuncSetAttribute(pyr_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
     if (e == cudaSuccess) max_smem_set = plan->smem_bytes;
   }
   if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
@@ -317,8 +325,14 @@ extern "C" void mimamo_pyr_plan_destroy(mimamo_pyr_plan* plan) {
   delete plan;
 }
 
+static size_t pyr_scratch_bytes(const mimamo_pyr_plan* plan) {
+  if (!plan->d.large) return 0;
+  return (size_t)plan->large_grid * ((size_t)plan->d.Kp * plan->d.Kp + plan->d.work_floats) * sizeof(float);
+}
+
 int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
-                     float* const* coeff_out, const int* root, cudaStream_t stream) {
+                     float* const* coeff_out, const int* root, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
   MM_REQUIRE(plan && frames && coeff_out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(n_windows >= 0 && T >= 1, MIMAMO_E_VALUE, "bad batch geometry");
   if (n_windows == 0) return MIMAMO_OK;
@@ -328,14 +342,28 @@ int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n
     MM_REQUIRE(coeff_out[i], MIMAMO_E_VALUE, "null output for level %d", i);
     outs.p[i] = coeff_out[i];
   }
-  pyr_build_kernel<<<(unsigned)(n_windows * T), kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root);
+  const long long n_frames = n_windows * T;
+  if (plan->d.large) {
+    const size_t need = pyr_scratch_bytes(plan);
+    MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
+    const unsigned grid = (unsigned)(n_frames < plan->large_grid ? n_frames : plan->large_grid);
+    pyr_build_kernel<true><<<grid, kPyrThreads, 0, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames);
+  } else {
+    pyr_build_kernel<false><<<(unsigned)n_frames, kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root, nullptr, n_frames);
+  }
   MM_LAUNCH_OK();
   return MIMAMO_OK;
 }
 
+extern "C" int mimamo_pyr_build_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T, size_t* bytes_out) {
+  MM_REQUIRE(plan && bytes_out, MIMAMO_E_VALUE, "null argument");
+  *bytes_out = pyr_scratch_bytes(plan);
+  return MIMAMO_OK;
+}
+
 extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows,
-                                int32_t T, float* const* coeff_out, void* stream) {
-  return pyr_build_launch(plan, frames, n_windows, T, coeff_out, nullptr, (cudaStream_t)stream);
+                                int32_t T, float* const* coeff_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return pyr_build_launch(plan, frames, n_windows, T, coeff_out, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // accessors used by the fused path in phase_tail.cu

@@ -149,3 +149,22 @@ def test_frame_dedup_is_exact(cuda, monkeypatch):
     ref = [O.extract(c) for c in O.build_pyramid(gray[idx], 4, 2, [1, 2])]
     for a, r in zip(dedup, ref):
         assert (a[idx].cpu() - r).abs().max() < PHASE_TOL
+
+
+def test_config3_large_frames(cuda):
+    """BASELINE config 3 shape: 224x224 frames, height=5 (3 oriented scales), 8 orientations.
+    Frames this large do not fit in shared memory; the persistent large-frame path is used."""
+    x = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(23))
+    pde = _pde(5, 8, [1, 2, 3])
+    got_c = pde.build_pyramid(x.to(cuda))
+    got_d = pde.phase_difference(x.to(cuda))
+    ref_c = O.build_pyramid(x, 5, 8, [1, 2, 3])
+    for i, (c, d, rc) in enumerate(zip(got_c, got_d, ref_c)):
+        assert c.shape == rc.shape == (2, 8, 3, 224 >> i, 224 >> i, 2)
+        assert (c.cpu() - rc).abs().max() < COEFF_TOL
+        rd = O.extract(rc)
+        err = (d.cpu() - rd).abs()
+        print("config3 level %d: phase max|err| %.2e" % (i, err.max().item()))
+        assert err.max() < PHASE_TOL
+    with pytest.raises(RuntimeError, match="Cannot build 7 levels, image too small."):
+        _pde(7, 8, [1]).build_pyramid(x.to(cuda))
