@@ -152,9 +152,16 @@ class Tester(object):
                 ready[k].record(copy)
 
         with torch.no_grad():
+            # the gray windows go first: nothing can start before they land, and the pyramid then
+            # overlaps the first RGB chunks
+            with torch.cuda.stream(copy):
+                gray = gray_windows.to(device, non_blocking=True)
+                gray_ready = torch.cuda.Event()
+                gray_ready.record(copy)
             for k in range(min(2, len(spans))):
                 issue(k)
-            gray = gray_windows.to(device, non_blocking=True)
+            main.wait_event(gray_ready)
+            gray.record_stream(main)
             phase_0, phase_1 = self.phase_diff_output(gray, self.phase_difference_extractor)
             feats = torch.empty((n, 2048), dtype=torch.float32, device=device)
             for k, (s, e) in enumerate(spans):

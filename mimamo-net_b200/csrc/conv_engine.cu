@@ -19,6 +19,7 @@
 #include "conv_engine.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -30,7 +31,8 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 constexpr int kEpiWarps = 16;                 // four per TMEM lane quarter, each owning a quarter of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 1 TMA warp + 1 MMA warp + epilogue warps
 constexpr int kResDepth = 2;                  // residual prefetch ring: chunks (32 columns) in flight per warp
-constexpr int kUmmaK = 16;
+constexpr int kUmmaK = 16;                  // elements per tcgen05.mma K step (umma_kblock issues kBlockK / kUmmaK = 4 of them)
+static_assert(kBlockK / kUmmaK == 4, "umma_kblock is written for four K steps");
 
 struct ConvParams {
   int mode;                 // 0: flat rows, 1: spatial boxes
@@ -159,6 +161,57 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// ---- lean issue-path helpers: 32-bit shared addresses, no address conversion in the loops ----
+__device__ __forceinline__ void bar_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 27)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void bar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma2d_u32(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma3d_u32(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma4d_u32(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void commit_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Four K=16 UMMAs of one 64-wide K block.  Descriptors are built from their 32-bit halves inside
+// PTX: lo = (address >> 4) field + constant LBO, hi = SBO/version/swizzle constant; +2 per K step.
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);    // bits [32,64): SBO = 64, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "add.u32 al, %1, 2;\n add.u32 bl, %2, 2;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+      "add.u32 al, %1, 4;\n add.u32 bl, %2, 4;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+      "add.u32 al, %1, 6;\n add.u32 bl, %2, 6;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   if (BF16) {
@@ -194,6 +247,12 @@ __device__ __forceinline__ int row_pixel(const ConvParams& p, int m_tile, int ro
     const long long q = (long long)m_tile * kBlockM + row;
     return q < p.M_total ? (int)q : -1;
   }
+  if (p.mode == 2) {                 // halo mode: rows run over the (W+2)-wide padded line, p.bw = W + 2
+    const int n = m_tile / p.tiles_h, th = m_tile - n * p.tiles_h;
+    const int dh = row / p.bw, dw = row - dh * p.bw;
+    const int h = th * p.bh + dh;
+    return (dh < p.bh && dw < p.Wo && h < p.Ho) ? (n * p.Ho + h) * p.Wo + dw : -1;
+  }
   const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
   const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
   const int per_img = p.bw * p.bh;
@@ -203,145 +262,14 @@ __device__ __forceinline__ int row_pixel(const ConvParams& p, int m_tile, int ro
   return (row < p.a_rows && n < p.Nimg && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
 }
 
+// Epilogue warps (shared by both kernels): TMEM -> registers (thread = output row) -> XOR-swizzled
+// fp32 staging in shared memory -> (lane = 8 channels of 8 rows) so that every global access is a
+// coalesced 16-byte vector.  The residual is prefetched by per-lane cp.async into a ring kResDepth
+// chunks deep that runs ahead ACROSS tiles (each lane later consumes exactly the bytes it fetched).
 template <int BLOCK_N, bool BF16, bool HAS_RES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvParams p) {
-  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
-  constexpr int STAGES = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * kAStageBytes;
-  uint8_t* sEpi = sB + STAGES * Cfg::kBStageBytes;
-  uint8_t* sRes = sEpi + Cfg::kEpiBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sRes + Cfg::kResBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = p.m_tiles * p.n_tiles;
-
-  if (warp == 0) {
-    {
-      // ------------------------------- TMA producer -------------------------------
-      // One lane issues every load, so the per-K-block instruction chain bounds the whole kernel
-      // (measured: ~940 cycles per K-block with integer divisions in the loop).  Everything is
-      // hoisted; the loop body is wait / expect_tx / two TMA issues.  The whole warp runs the loop
-      // (warp-uniform control flow => uniform registers), one elected lane issues.
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes;
-      const int n_tiles = p.n_tiles, mode = p.mode, cin_blocks = p.cin_blocks, taps_w = p.taps_w;
-      const int taps_h = p.num_k_blocks / (cin_blocks * taps_w);
-      const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
-      const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
-      const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB), full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
-      const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
-#pragma unroll 1
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
-        const int n0 = n_tile * BLOCK_N;
-        int c1 = 0, c2 = 0, c3 = 0;
-        if (mode == 0) {
-          c1 = m_tile * kBlockM;
-        } else {
-          const int tw = m_tile % tiles_w, rest = m_tile / tiles_w;
-          const int th = rest % tiles_h, tn = rest / tiles_h;
-          c1 = tw * step_w - pad;
-          c2 = th * step_h - pad;
-          c3 = tn * bn;
-        }
-        int kcol = 0;                                          // K offset into the weight matrix
-#pragma unroll 1
-        for (int kh = 0; kh < taps_h; ++kh) {
-#pragma unroll 1
-          for (int kw = 0; kw < taps_w; ++kw) {
-#pragma unroll 1
-            for (int cb = 0; cb < cin_blocks; ++cb, kcol += kBlockK) {
-              const uint32_t fb = full_u32 + stage * 8, eb = empty_u32 + stage * 8;
-              {
-                uint32_t spins = 0;
-                uint32_t ok;
-                do {
-                  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                               : "=r"(ok) : "r"(eb), "r"(phase ^ 1) : "memory");
-                  if (!ok && ++spins > (1u << 27)) __trap();
-                } while (!ok);
-              }
-              const uint32_t dstA = sA_u32 + stage * kAStageBytes, dstB = sB_u32 + stage * Cfg::kBStageBytes;
-              if (elect_one()) {
-              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx_bytes) : "memory");
-              if (mode == 0) {
-                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                             ::"r"(dstA), "l"(mapA), "r"(fb), "r"(cb * kBlockK), "r"(c1) : "memory");
-              } else {
-                asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                             ::"r"(dstA), "l"(mapA), "r"(fb), "r"(cb * kBlockK), "r"(c1 + kw), "r"(c2 + kh), "r"(c3) : "memory");
-              }
-              asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                           ::"r"(dstB), "l"(mapB), "r"(fb), "r"(kcol), "r"(n0) : "memory");
-              }
-              __syncwarp();
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      // ------------------------------- MMA issuer ---------------------------------
-      int stage = 0; uint32_t phase = 0;
-      int local = 0;
-      const int nkb = p.num_k_blocks;
-      const uint32_t idesc = p.idesc;
-      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA)), b_desc0 = make_smem_desc(smem_u32(sB));
-#pragma unroll 1
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1;
-        const uint32_t acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-#pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          // stage offsets in the descriptors' (address >> 4) field; +2 per 16-element K step
-          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kAStageBytes >> 4));
-          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (Cfg::kBStageBytes >> 4));
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);                  // frees the smem stage when the MMAs retire
-            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    // --------------------------------- epilogue -----------------------------------
-    // TMEM -> registers (thread = output row) -> XOR-swizzled fp32 staging in shared memory ->
-    // (lane = 8 channels of 8 rows) so that every global access is a coalesced 16-byte vector.
-    // The residual is prefetched by per-lane cp.async into a ring kResDepth chunks deep that runs
-    // ahead ACROSS tiles (each lane later consumes exactly the bytes it fetched: no extra sync).
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, int lane, uint8_t* sEpi, uint8_t* sRes,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
+                                               int num_tiles) {
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per TMEM quarter (64-wide tiles: 2)
@@ -452,6 +380,277 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (HAS_RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+}
+
+template <int BLOCK_N, bool BF16, bool HAS_RES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvParams p) {
+  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStageBytes;
+  uint8_t* sEpi = sB + STAGES * Cfg::kBStageBytes;
+  uint8_t* sRes = sEpi + Cfg::kEpiBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sRes + Cfg::kResBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  // The issue warps execute a strictly serial instruction stream: at ~5 cycles per dependent
+  // instruction their loop length, not TMA or the tensor pipe, bounded the first versions of this
+  // kernel (~600 cycles per K block, ncu source view).  Both loops are therefore kept minimal:
+  // election hoisted, addresses advanced incrementally, descriptors built from 32-bit halves.
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    const bool leader = elect_one();
+    const uint32_t tx_bytes = (uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes;
+    const int n_tiles = p.n_tiles, mode = p.mode, cin_blocks = p.cin_blocks, taps_w = p.taps_w;
+    const int taps_h = p.num_k_blocks / (cin_blocks * taps_w);
+    const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+    const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    int stage = 0; uint32_t parity = 1;                        // producer waits on empty with parity phase ^ 1
+    uint32_t dA = sA0, dB = sB0, fb = full0, eb = empty0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      const int n0 = n_tile * BLOCK_N;
+      int c1 = 0, c2 = 0, c3 = 0;
+      if (mode == 0) {
+        c1 = m_tile * kBlockM;
+      } else {
+        const int tw = m_tile % tiles_w, rest = m_tile / tiles_w;
+        const int th = rest % tiles_h, tn = rest / tiles_h;
+        c1 = tw * step_w - pad;
+        c2 = th * step_h - pad;
+        c3 = tn * bn;
+      }
+      int kcol = 0;                                            // K offset into the weight matrix
+#pragma unroll 1
+      for (int kh = 0; kh < taps_h; ++kh) {
+#pragma unroll 1
+        for (int kw = 0; kw < taps_w; ++kw) {
+#pragma unroll 1
+          for (int cb = 0; cb < cin_blocks; ++cb, kcol += kBlockK) {
+            bar_wait_u32(eb, parity);
+            if (leader) {
+              bar_expect_tx_u32(fb, tx_bytes);
+              if (mode == 0) tma2d_u32(dA, mapA, fb, cb * kBlockK, c1);
+              else tma4d_u32(dA, mapA, fb, cb * kBlockK, c1 + kw, c2 + kh, c3);
+              tma2d_u32(dB, mapB, fb, kcol, n0);
+            }
+            if (++stage == STAGES) { stage = 0; parity ^= 1; dA = sA0; dB = sB0; fb = full0; eb = empty0; }
+            else { dA += kAStageBytes; dB += Cfg::kBStageBytes; fb += 8; eb += 8; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    const int nkb = p.num_k_blocks;
+    const uint32_t idesc = p.idesc;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    int stage = 0; uint32_t parity = 0;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0, fb = full0, eb = empty0;
+    int local = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1;
+      bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        bar_wait_u32(fb, parity);
+        tc_fence_after();
+        if (leader) {
+          umma_kblock(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+          commit_u32(eb);                                      // frees the smem stage when the MMAs retire
+          if (kb == nkb - 1) commit_u32(tfull0 + acc * 8);
+        }
+        if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
+        else { a_lo += kAStageBytes >> 4; b_lo += Cfg::kBStageBytes >> 4; fb += 8; eb += 8; }
+      }
+    }
+  } else {
+    epilogue_warps<BLOCK_N, BF16, HAS_RES>(p, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Halo-resident 3x3 (stride 1, pad 1) convolution.
+//
+// The box-per-tap kernel above moves every activation nine times from L2 to shared memory (ncu:
+// 727 MB through l1tex__m_xbar2l1tex for a 51 MB tensor) and is bound by that fabric (~42 B/clk/SM)
+// for Cout <= 128.  Here the (bh+2) x (W+2) x 64-channel input patch of a tile of bh full output rows
+// is loaded ONCE per channel block; output rows are indexed along the padded line (m = dh*(W+2)+dw,
+// the two extra columns per line are discarded), so tap (kh,kw) is the SAME shared-memory tile
+// read through a UMMA descriptor whose start address is shifted by (kh*(W+2)+kw) rows (the 128B
+// swizzle is keyed on absolute shared-memory address bits, so a shifted start needs nothing else --
+// verified on B200: base_offset = 0 is correct, (addr >> 7) & 7 is not).  Activations
+// and weights use separate rings (one patch feeds nine weight boxes).
+// ---------------------------------------------------------------------------------------
+constexpr int kHaloABytes = 32768;            // (bh+2)*(W+2) <= 256 patch pixels x 128 B
+constexpr int kHaloAStages = 2;
+
+template <int BLOCK_N>
+struct HaloCfg {
+  static constexpr int kBStageBytes = 3 * BLOCK_N * kBlockK * 2;          // the three taps of one kernel row
+  static constexpr int kEpiBytes = kEpiWarps * 32 * 128;
+  static constexpr int kBStages = (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes > 6
+                                      ? 6 : (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kHaloAStages * kHaloABytes + kBStages * kBStageBytes + kEpiBytes + 512 + 1024;
+  static_assert(kBStages >= 2, "weight ring needs at least two stages");
+};
+
+template <int BLOCK_N, bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ ConvParams p) {
+  using Cfg = HaloCfg<BLOCK_N>;
+  constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SA * kHaloABytes;
+  uint8_t* sEpi = sB + SB * Cfg::kBStageBytes;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sEpi + Cfg::kEpiBytes);
+  uint64_t* empty_a = full_a + SA;
+  uint64_t* full_b = empty_a + SA;
+  uint64_t* empty_b = full_b + SB;
+  uint64_t* tmem_full = empty_b + SB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int cin_blocks = p.cin_blocks, n_tiles = p.n_tiles, tiles_h = p.tiles_h, bh = p.bh, line = p.bw;   // line = W + 2
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    const bool leader = elect_one();
+    const uint32_t a_bytes = (uint32_t)p.a_rows * 128u;      // (bh+2)*(W+2) patch pixels
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+    const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a), fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
+    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    int sa = 0, sb = 0; uint32_t pa = 1, pb = 1;
+    // patches are issued one (tile, channel block) ahead of the weights that consume them
+    int nt = blockIdx.x, ncb = 0;                            // next patch to issue
+    auto issue_patch = [&]() {
+      if (nt >= num_tiles) return;
+      const int m_tile = nt / n_tiles;
+      const int n_img = m_tile / tiles_h, th = m_tile - n_img * tiles_h;
+      bar_wait_u32(ea0 + sa * 8, pa);
+      if (leader) {
+        bar_expect_tx_u32(fa0 + sa * 8, a_bytes);
+        tma4d_u32(sA0 + sa * kHaloABytes, mapA, fa0 + sa * 8, ncb * kBlockK, -1, th * bh - 1, n_img);
+      }
+      if (++sa == SA) { sa = 0; pa ^= 1; }
+      if (++ncb == cin_blocks) { ncb = 0; nt += gridDim.x; }
+    };
+    issue_patch();
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n0 = (tile % n_tiles) * BLOCK_N;
+#pragma unroll 1
+      for (int cb = 0; cb < cin_blocks; ++cb) {
+        issue_patch();                                         // next (tile, cb) patch, if any
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {                       // one box = the three taps of a kernel row
+          bar_wait_u32(eb0 + sb * 8, pb);
+          if (leader) {
+            bar_expect_tx_u32(fb0 + sb * 8, (uint32_t)Cfg::kBStageBytes);
+            tma3d_u32(sB0 + sb * Cfg::kBStageBytes, mapB, fb0 + sb * 8, cb * kBlockK, n0, kh * 3);
+          }
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    const uint32_t idesc = p.idesc;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+    const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a), fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    const uint32_t row16 = (uint32_t)line * 8u;              // one padded line in (address >> 4) units
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+    int local = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1;
+      bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+      for (int cb = 0; cb < cin_blocks; ++cb) {
+        bar_wait_u32(fa0 + sa * 8, pa);
+        uint32_t a_row = a_lo0 + sa * (kHaloABytes >> 4);    // shifted views of the same patch: +kw rows, +kh lines
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh, a_row += row16) {
+          bar_wait_u32(fb0 + sb * 8, pb);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStageBytes >> 4);
+            umma_kblock(d_tmem, a_row, b_lo, idesc, (cb | kh) != 0 ? 1u : 0u);
+            umma_kblock(d_tmem, a_row + 8, b_lo + (BLOCK_N * 128 >> 4), idesc, 1u);
+            umma_kblock(d_tmem, a_row + 16, b_lo + 2 * (BLOCK_N * 128 >> 4), idesc, 1u);
+            commit_u32(eb0 + sb * 8);
+            if (kh == 2) {
+              commit_u32(ea0 + sa * 8);
+              if (cb == cin_blocks - 1) commit_u32(tfull0 + acc * 8);
+            }
+          }
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else {
+    epilogue_warps<BLOCK_N, BF16, false>(p, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -570,6 +769,43 @@ static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b
   return MIMAMO_E_RUNTIME;
 }
 
+template <int BLOCK_N, bool BF16>
+static int launch_halo_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = HaloCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BLOCK_N, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t a0, a1;
+      MM_CUDA(cudaEventCreate(&a0));
+      MM_CUDA(cudaEventCreate(&a1));
+      g_prof_events.emplace_back(a0, a1);
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
+    MM_CUDA(cudaEventRecord(e0, stream));
+  }
+  conv3x3_halo_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
+  MM_LAUNCH_OK();
+  if (e1) MM_CUDA(cudaEventRecord(e1, stream));
+  return MIMAMO_OK;
+}
+
+// MIMAMO_CONV3X3_HALO: 0 = box-per-tap only; 1 = halo mode (default).  Round-1 experiment on B200: setting the
+// descriptor's base_offset field to (addr >> 7) & 7 for the row-shifted views gives WRONG results; the 128B
+// swizzle is a function of the absolute shared-memory address, so base_offset stays 0.
+static int halo_setting() {
+  const char* e = getenv("MIMAMO_CONV3X3_HALO");
+  return e ? atoi(e) : 1;
+}
+
 int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, const float* shift_host, int Cout,
                     int Cin, int ksize, int stride, int pad, int relu, ElemType elem) {
   MM_REQUIRE(Cout % 64 == 0, MIMAMO_E_RUNTIME, "Cout=%d must be a multiple of 64 for the tcgen05 engine", Cout);
@@ -650,6 +886,46 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   MM_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ld_res % 8 == 0), MIMAMO_E_VALUE, "row pitches must be multiples of 8");
   if (B == 0) return MIMAMO_OK;
   const int Ho = out_size(H, L.ksize, L.stride, L.pad), Wo = out_size(W, L.ksize, L.stride, L.pad);
+  // fill-bound 3x3 layers (Cout <= 128): halo-resident kernel
+  if (halo_setting() != 0 && L.ksize == 3 && L.stride == 1 && L.pad == 1 && residual == nullptr && L.block_n <= 128 &&
+      W + 2 <= 64) {
+    const int line = W + 2;
+    int bh = kBlockM / line;
+    if (bh > H) bh = H;
+    while ((bh + 2) * line > kHaloABytes / 128) --bh;
+    if (bh >= 1) {
+      CUtensorMap ma, mb;
+      const uint64_t dims[4] = {(uint64_t)L.Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)L.Cin_p * 2, (uint64_t)W * L.Cin_p * 2, (uint64_t)H * W * L.Cin_p * 2};
+      const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)line, (uint32_t)(bh + 2), 1};
+      const uint32_t es[4] = {1, 1, 1, 1};
+      int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
+      if (rc) return rc;
+      ConvParams p;
+      memset(&p, 0, sizeof(p));
+      const int bn_cols = fill_common(p, L, out, ldc, nullptr, 0);
+      {
+        // weights viewed as [tap][Cout][Cin_p]: one box = the three taps of a kernel row, each tap's
+        // [BLOCK_N][64] tile contiguous in shared memory
+        const uint64_t K = (uint64_t)9 * L.Cin_p;
+        const uint64_t wdims[3] = {(uint64_t)L.Cin_p, (uint64_t)L.Cout, 9};
+        const uint64_t wstr[2] = {K * 2, (uint64_t)L.Cin_p * 2};
+        const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)bn_cols, 3};
+        const uint32_t wes[3] = {1, 1, 1};
+        rc = encode_map(&mb, L.elem, 3, L.w_dev, wdims, wstr, wbox, wes);
+        if (rc) return rc;
+      }
+      p.mode = 2;
+      p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
+      p.bw = line; p.bh = bh; p.bn = 1;
+      p.tiles_w = 1; p.tiles_h = (Ho + bh - 1) / bh;
+      p.a_rows = (bh + 2) * line;
+      p.m_tiles = p.tiles_h * B;
+      const bool bf = L.elem == kBF16;
+      if (L.block_n == 64) return bf ? launch_halo_cfg<64, true>(ma, mb, p, stream) : launch_halo_cfg<64, false>(ma, mb, p, stream);
+      return bf ? launch_halo_cfg<128, true>(ma, mb, p, stream) : launch_halo_cfg<128, false>(ma, mb, p, stream);
+    }
+  }
   // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows
   int best_bw = 1, best_bh = 1, best_bn = 1;
   long long best_tiles = -1;
