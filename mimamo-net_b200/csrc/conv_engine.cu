@@ -661,6 +661,126 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------
+// conv1_7x7_s2 as a "line" kernel.  After space-to-depth the layer is a 4x4 / stride-1 convolution
+// over 16-channel pixels (32 bytes).  One tile = one output line (112 pixels): the 4 x 115-pixel input
+// patch is loaded once (14.7 KB, SWIZZLE_32B rows of one pixel each) and each of the 16 taps is a
+// K=16 UMMA on a row-shifted view of it; the whole 64 x 256 weight matrix (32 KB) stays resident.
+// Compared with materialising the 4 overlapping 128-byte windows per pixel through TMA (the
+// conv_gemm_kernel path, 96 KB of L2->SM fill per 128 pixels) the fill drops to 14.7 KB per line.
+// ---------------------------------------------------------------------------------------
+constexpr int kLineABytes = 16384;
+constexpr int kLineAStages = 6;
+constexpr int kLineWBytes = 32768;
+constexpr uint32_t kDescHi32 = 16u | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
+constexpr int kLineSmemBytes = kLineWBytes + kLineAStages * kLineABytes + kEpiWarps * 32 * 128 + 512 + 1024;
+
+__device__ __forceinline__ void umma_one(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t hi) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+      : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvParams p) {
+  constexpr int SA = kLineAStages, BLOCK_N = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + kLineWBytes;
+  uint8_t* sEpi = sA + SA * kLineABytes;
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * 32 * 128);
+  uint64_t* empty_a = full_a + SA;
+  uint64_t* w_full = empty_a + SA;
+  uint64_t* tmem_full = w_full + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * 2); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = p.m_tiles;                           // one N tile (Cout = 64)
+  const int lines = p.tiles_h, line = p.bw;                  // 112 output lines per image, 115-pixel padded line
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t a_bytes = (uint32_t)p.a_rows * 32u;       // 4 * 115 pixels
+    const uint32_t sA0 = smem_u32(sA), fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
+    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    if (leader) {
+      bar_expect_tx_u32(smem_u32(w_full), (uint32_t)kLineWBytes);
+      tma3d_u32(smem_u32(sW), mapB, smem_u32(w_full), 0, 0, 0);
+    }
+    int sa = 0; uint32_t pa = 1;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_img = tile / lines, h = tile - n_img * lines;
+      bar_wait_u32(ea0 + sa * 8, pa);
+      if (leader) {
+        bar_expect_tx_u32(fa0 + sa * 8, a_bytes);
+        tma4d_u32(sA0 + sa * kLineABytes, mapA, fa0 + sa * 8, 0, 0, h, n_img);
+      }
+      if (++sa == SA) { sa = 0; pa ^= 1; }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = p.idesc;
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), w_lo0 = desc_lo(smem_u32(sW));
+    const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    bar_wait_u32(smem_u32(w_full), 0);
+    int sa = 0; uint32_t pa = 0;
+    int local = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1;
+      bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
+      bar_wait_u32(fa0 + sa * 8, pa);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t a_base = a_lo0 + sa * (kLineABytes >> 4);
+#pragma unroll
+        for (int kh = 0; kh < 4; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 4; ++kw)
+            umma_one(d_tmem, a_base + (uint32_t)(kh * line + kw) * 2u, w_lo0 + (uint32_t)(kh * 4 + kw) * 128u, idesc,
+                     (kh | kw) != 0 ? 1u : 0u, kDescHi32);
+        commit_u32(ea0 + sa * 8);
+        commit_u32(tfull0 + acc * 8);
+      }
+      if (++sa == SA) { sa = 0; pa ^= 1; }
+    }
+  } else {
+    epilogue_warps<BLOCK_N, BF16, false>(p, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -680,14 +800,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, ElemType elem, int rank, const void* base, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* estr,
+                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   MM_REQUIRE(fn, MIMAMO_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bd[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bd[i] = box[i]; es[i] = estr[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(map, elem == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
-                  const_cast<void*>(base), gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  const_cast<void*>(base), gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MM_REQUIRE(r == CUDA_SUCCESS, MIMAMO_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box %u %u %u %u)",
              (int)r, rank, box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
@@ -756,7 +877,14 @@ static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& 
 
 // BLOCK_N actually launched: residual layers use at most 128 columns (the residual ring takes the
 // shared memory of two 256-wide pipeline stages).
-static int effective_block_n(const ConvLayer& L, bool has_res) { return (has_res && L.block_n > 128) ? 128 : L.block_n; }
+static int effective_block_n(const ConvLayer& L, bool has_res) {
+  static int res_bn = 0;
+  if (!res_bn) {
+    const char* e = getenv("MIMAMO_RES_BLOCK_N");
+    res_bn = (e && atoi(e) == 128) ? 128 : 256;      // 256: each tile writes whole 512-byte pixel rows (measured 33.3 -> 32.4 ms per 2048 images)
+  }
+  return (has_res && L.block_n > res_bn) ? res_bn : L.block_n;
+}
 
 static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
   const bool bf = L.elem == kBF16, res = p.residual != nullptr;
@@ -968,7 +1096,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
 // 64 contiguous 16-bit values = exactly one 128-byte K block.  The activation tensor map therefore
 // addresses OVERLAPPING windows: dim1 = output column with a 32-byte global stride and a 128-byte
 // extent.  K = 4 rows x 64 = 256 (147 real taps, the rest zero weights).
-int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
+static int conv1_s2d_forward_windows(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
   MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [Cout][256] layer");
   if (B == 0) return MIMAMO_OK;
   const int Wo = 112, Ho = 112, S2D = 115;
@@ -993,6 +1121,69 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
   p.a_rows = bw * bh;
   p.m_tiles = p.tiles_w * p.tiles_h * B;
   return launch(L, ma, mb, p, stream);
+}
+
+
+// conv1 over the space-to-depth'ed input: line kernel by default, overlapping-window GEMM with
+// MIMAMO_CONV1_LINE=0 (kept as the cross-check of the line kernel).
+int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
+  MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1 && L.Cout == 64, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [64][256] layer");
+  const char* e = getenv("MIMAMO_CONV1_LINE");
+  if (e && e[0] == '0') return conv1_s2d_forward_windows(L, s2d, B, out, ldc, stream);
+  if (B == 0) return MIMAMO_OK;
+  const int S2D = 115, Wo = 112, Ho = 112;
+  CUtensorMap ma, mb;
+  {
+    const uint64_t dims[4] = {16, (uint64_t)S2D, (uint64_t)S2D, (uint64_t)B};
+    const uint64_t strides[3] = {32, (uint64_t)S2D * 32, (uint64_t)S2D * S2D * 32};
+    const uint32_t box[4] = {16, (uint32_t)S2D, 4, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode_map(&ma, L.elem, 4, s2d, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+    // weights [64][256] viewed as [tap (16)][n (64)][16 ch]: one box = the whole matrix, tap-major in smem
+    const uint64_t wdims[3] = {16, 64, 16};
+    const uint64_t wstr[2] = {512, 32};
+    const uint32_t wbox[3] = {16, 64, 16};
+    const uint32_t wes[3] = {1, 1, 1};
+    rc = encode_map(&mb, L.elem, 3, L.w_dev, wdims, wstr, wbox, wes, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (rc) return rc;
+  }
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  fill_common(p, L, out, ldc, nullptr, 0);
+  p.mode = 2;
+  p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
+  p.bw = S2D; p.bh = 1; p.bn = 1;
+  p.tiles_w = 1; p.tiles_h = Ho;
+  p.a_rows = 4 * S2D;
+  p.m_tiles = Ho * B; p.n_tiles = 1;
+  p.num_k_blocks = 4;                                        // K = 256 for the flop accounting
+  static bool attr_set[2] = {false, false};
+  const bool bf = L.elem == kBF16;
+  if (!attr_set[bf]) {
+    if (bf) MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    else MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    attr_set[bf] = true;
+  }
+  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t a0, a1;
+      MM_CUDA(cudaEventCreate(&a0));
+      MM_CUDA(cudaEventCreate(&a1));
+      g_prof_events.emplace_back(a0, a1);
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * 64.0 * 256.0;
+    MM_CUDA(cudaEventRecord(e0, stream));
+  }
+  if (bf) conv1_line_kernel<true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, p);
+  else conv1_line_kernel<false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, p);
+  MM_LAUNCH_OK();
+  if (e1) MM_CUDA(cudaEventRecord(e1, stream));
+  return MIMAMO_OK;
 }
 
 }  // namespace mimamo
