@@ -3,9 +3,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the full hot path (steerable pyramid + phase difference, ResNet50 pool5,
-two-stream GRU head) over BASELINE.json configs[1]: 32 synthetic 64-frame clips per GPU = 2048
-face-windows (gray windows (32,64,13,48,48) fp32, RGB (2048,3,224,224) fp32, seeded weights).
+A step = one pass of the full hot path (face-crop preprocessing, steerable pyramid + phase
+difference, ResNet50 pool5, two-stream GRU head) over BASELINE.json configs[1]: 32 synthetic
+64-frame 112x112 clips per GPU = 2048 face-windows (uint8 crops (32,64,112,112,3), seeded weights).
+`value` times Tester.infer_crops with the crops resident in HBM, `e2e` times Tester.infer_crops_host
+from pinned host memory; `float_inputs` reports the same two legs through the fp32-tensor entry
+points (Tester.infer_clips / infer_clips_host: gray windows (32,64,13,48,48) + RGB (2048,3,224,224)
+prepared on the host, the tensors the reference's DataLoader ships to the GPU).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
 """
 import argparse
@@ -141,7 +145,7 @@ def main():
     mimamo_b200.install()
     import _native
     from tester import Tester
-    from bench_inputs import make_inputs, synthetic_weights
+    from bench_inputs import make_crops, make_inputs, synthetic_weights
 
     dev = torch.device("cuda", local)
     if world > 1:
@@ -151,23 +155,25 @@ def main():
 
     resnet_sd, head_sd = synthetic_weights()
     tester = Tester(None, batch_size=CLIPS, resnet_model=resnet_sd, head_state_dict=head_sd)
-    gray_h, rgb_h = make_inputs(seed=100 + rank, clips=CLIPS, frames=FRAMES, t=T, size=SIZE)   # pinned host buffers
-    gray_d, rgb_d = gray_h.to(dev), rgb_h.to(dev)
+    crops_h = make_crops(seed=100 + rank, clips=CLIPS, frames=FRAMES)                         # pinned host buffer
+    crops_d = crops_h.to(dev)
     gathered = torch.empty(world * CLIPS, FRAMES, 2, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                             # > 126 MB L2
 
-    def step_device():
-        out = tester.infer_clips(gray_d, rgb_d)
+    def finish(out, to_host):
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)          # per-video predictions to every rank
-        return out
+            return gathered.cpu() if to_host else gathered
+        return out.cpu() if to_host else out
+
+    def step_device():
+        flush.zero_()                                           # the 77 MB of crops must not survive in L2 between steps
+        return finish(tester.infer_crops(crops_d), False)
 
     def step_e2e():
-        # the public host-facing call: pinned host buffers in, host predictions out; the RGB copy is
-        # chunked on a copy stream inside infer_clips_host and overlaps the compute of earlier chunks
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, tester.infer_clips_host(gray_h, rgb_h, to_host=False))
-            return gathered.cpu()
-        return tester.infer_clips_host(gray_h, rgb_h)
+        # the public host-facing call: pinned host crops in, host predictions out
+        flush.zero_()
+        return finish(tester.infer_crops_host(crops_h, to_host=False), True)
 
     def barrier():
         torch.cuda.synchronize()
@@ -208,18 +214,37 @@ def main():
 
     with torch.no_grad():
         pde, rn, hd = tester.phase_difference_extractor, tester.resnet50_extractor, tester.model
-        p0, p1 = tester.phase_diff_output(gray_d, pde)
-        feats = rn.features(rgb_d).view(CLIPS, FRAMES, 2048)
-        stages = {"pyramid_phase_ms": stage_ms(lambda: tester.phase_diff_output(gray_d, pde)),
-                  "resnet50_ms": stage_ms(lambda: rn.features(rgb_d)),
+        pre = tester.crop_preprocessor()
+        flat = crops_d.view(WINDOWS, 112, 112, 3)
+        widx = tester.clip_window_index(CLIPS, FRAMES, dev)
+
+        def pyramid_stage():
+            return pde.phase_difference_indexed(pre.gray(flat), widx)
+
+        p0, p1 = [d.view(CLIPS, FRAMES, -1, d.shape[-2], d.shape[-1]) for d in pyramid_stage()]
+        feats = rn.features_from_crops(flat, pre).view(CLIPS, FRAMES, 2048)
+        stages = {"pyramid_phase_ms": stage_ms(pyramid_stage),
+                  "resnet50_ms": stage_ms(lambda: rn.features_from_crops(flat, pre)),
                   "head_ms": stage_ms(lambda: hd([p0, p1], feats))}
         del p0, p1, feats
+    float_inputs = None
     if args.quick:
         e2e_ms = float("nan")
     else:
         for _ in range(2):
             step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
+        # the fp32-tensor entry points (what the reference's DataLoader would hand over), fewer steps
+        gray_h, rgb_h = make_inputs(seed=100 + rank, clips=CLIPS, frames=FRAMES, t=T, size=SIZE)
+        gray_d, rgb_d = gray_h.to(dev), rgb_h.to(dev)
+        n_f = max(2, min(args.steps, 4))
+        tester.infer_clips(gray_d, rgb_d)
+        f_dev = timed(lambda: finish(tester.infer_clips(gray_d, rgb_d), False), n_f)
+        tester.infer_clips_host(gray_h, rgb_h)
+        f_e2e = timed(lambda: finish(tester.infer_clips_host(gray_h, rgb_h, to_host=False), True), n_f)
+        float_inputs = {"value": world * WINDOWS * n_f / (f_dev / 1e3), "e2e": world * WINDOWS * n_f / (f_e2e / 1e3),
+                        "unit": UNIT, "steps": n_f, "h2d_bytes_per_step": world * (gray_h.numel() + rgb_h.numel()) * 4}
+        del gray_d, rgb_d
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -233,11 +258,12 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[1]: full MIMAMO inference (SCFpyr+phase, ResNet50 pool5, 2-stream GRU) on "
-                               "32 synthetic 64-frame clips per GPU = 2048 face-windows/step/GPU",
-                   "dtypes": "pyramid+phase f32, ResNet50 bf16 (f32 accumulate), PhaseNet f16, dense+GRU f32",
-                   "l2": "inputs (1.48 GB/step/GPU) exceed the 126 MB L2", "videos_sharded_by": "rank"},
+                               "32 synthetic 64-frame 112x112 clips per GPU = 2048 face-windows/step/GPU",
+                   "inputs": "uint8 face crops (32,64,112,112,3) per GPU; PIL-exact preprocessing on the device",
+                   "dtypes": "preprocessing u8/int32, pyramid+phase f32, ResNet50 bf16 (f32 accumulate), PhaseNet f16, dense+GRU f32",
+                   "l2": "a 256 MB buffer is rewritten before every timed step (L2 flush)", "videos_sharded_by": "rank"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": world * (gray_h.numel() + rgb_h.numel()) * 4,
+                "h2d_bytes_per_step": world * crops_h.numel(),
                 "d2h_bytes_per_step": world * (world if world > 1 else 1) * CLIPS * FRAMES * 2 * 4},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: ResNet50 + PhaseNet convs)",
@@ -250,6 +276,8 @@ def main():
         "stage_ms": stages,
         "clocks": sampler.summary(),
     }
+    if float_inputs is not None:
+        line["float_inputs"] = float_inputs
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         v, stages, cores = cpu_reference_rate()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

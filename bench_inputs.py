@@ -24,6 +24,14 @@ def make_inputs(seed, clips, frames, t, size):
     return gray, rgb
 
 
+def make_crops(seed, clips, frames, size=112):
+    """uint8 face crops (clips, frames, size, size, 3), uniform 0-255: what OpenFace's aligned bmp files
+    decode to (BASELINE.json configs[1]: synthetic 64-frame 112x112 clips).  Pinned host tensor."""
+    g = torch.Generator().manual_seed(seed)
+    crops = torch.randint(0, 256, (clips, frames, size, size, 3), generator=g, dtype=torch.uint8)
+    return crops.pin_memory() if torch.cuda.is_available() else crops
+
+
 def _fill(spec, seed, gain=1.0):
     g = torch.Generator().manual_seed(seed)
     sd = {}

@@ -98,6 +98,44 @@ int mimamo_pyr_phase_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_wind
 int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
                      float* const* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Clip variant of P3: every distinct frame is transformed once and
+ * window w, slot t reads frame window_index[w*T + t] -- the clamp-window rule of
+ * api/sampler/snippet_sampler.py:144-152, built by the caller.  Bit-identical to materialising
+ * the windows and calling mimamo_pyr_phase.
+ * frames f32[n_frames,H,H], window_index i32[n_windows*T] (device)
+ * -> out[level] f32[n_windows, nbands*(T-1), c, c]. */
+int mimamo_pyr_phase_indexed_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_frames,
+                                             int64_t n_windows, int32_t T, size_t* bytes_out);
+int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float* frames, int64_t n_frames,
+                             const int32_t* window_index, int64_t n_windows, int32_t T,
+                             float* const* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Face-crop preprocessing on the device, bit-exact with the
+ * reference's PIL / torchvision transforms:
+ *   gray: Image.convert('L') -> Resize(gray_size, LANCZOS) -> float / 255
+ *         (api/sampler/snippet_sampler.py:156-185, api/utils/data_utils.py:71-120)
+ *   RGB : Resize(resize) [PIL bilinear] -> CenterCrop(crop) -> ToTensor -> x*255 -> Normalize(mean, 1)
+ *         (api/utils/model_utils.py:26-40, api/sampler/image_sampler.py:118-119)
+ * The tap tables are Pillow's (libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc:
+ * per output index a first input index, a tap count and 22-bit fixed-point taps), built on the
+ * host by api/utils/pil_tables.py.  bounds i32[out][2], kk i32[out][taps].
+ * crops u8[n, src, src, 3] (RGB, HWC as OpenFace's bmp files decode).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mimamo_preproc mimamo_preproc;
+int  mimamo_preproc_create(int32_t src, int32_t gray_size, int32_t gray_taps,
+                           const int32_t* gray_bounds_host, const int32_t* gray_kk_host,
+                           int32_t resize, int32_t rgb_taps,
+                           const int32_t* rgb_bounds_host, const int32_t* rgb_kk_host,
+                           int32_t crop, int32_t crop_off, const float* mean_host /* [3] */,
+                           mimamo_preproc** plan_out);
+void mimamo_preproc_destroy(mimamo_preproc* plan);
+int  mimamo_preproc_geometry(const mimamo_preproc* plan, int32_t* src, int32_t* gray_size, int32_t* crop);
+/* -> out f32[n, gray_size, gray_size] in [0,1] */
+int  mimamo_crops_to_gray(const mimamo_preproc* plan, const uint8_t* crops, int64_t n, float* out, void* stream);
+/* -> out f32[n, 3, crop, crop] = (u8/255)*255 - mean, what Image_Sampler yields */
+int  mimamo_crops_to_rgb(const mimamo_preproc* plan, const uint8_t* crops, int64_t n, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Convolution network engine (rows R and H of SURVEY.md section 8(a)).
  * A net is a flat table of named host tensors (the reference-keyed state_dict) folded once
@@ -121,6 +159,12 @@ void mimamo_resnet50_destroy(mimamo_resnet50* net);
 int  mimamo_resnet50_workspace_bytes(const mimamo_resnet50* net, int32_t batch, size_t* bytes_out);
 int  mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x, int32_t batch, float* out,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, from uint8 face crops [B, src, src, 3]: the RGB transform above runs on the device and
+ * feeds conv1 directly (workspace as mimamo_resnet50_workspace_bytes). */
+int  mimamo_resnet50_pool5_crops(const mimamo_resnet50* net, const mimamo_preproc* plan,
+                                 const uint8_t* crops, int32_t batch, float* out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* H: two-stream head.  Replaces Two_Stream_RNN.forward (api/mimamo_net.py:129-143; MLP :22-26,
  * PhaseNet :79-95; GRU built without batch_first at :119, so it recurs over dim 0 = bs).

@@ -50,6 +50,18 @@ _SIGNATURES = {
                                                         ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_pyr_phase": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(vp), vp,
                                         ctypes.c_size_t, vp]),
+    "mimamo_pyr_phase_indexed_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                                                ctypes.POINTER(ctypes.c_size_t)]),
+    "mimamo_pyr_phase_indexed": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.c_int32,
+                                                ctypes.POINTER(vp), vp, ctypes.c_size_t, vp]),
+    "mimamo_preproc_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int32_p,
+                                             ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int32_p, ctypes.c_int32,
+                                             ctypes.c_int32, c_float_p, ctypes.POINTER(vp)]),
+    "mimamo_preproc_destroy": (None, [vp]),
+    "mimamo_preproc_geometry": (ctypes.c_int, [vp, c_int32_p, c_int32_p, c_int32_p]),
+    "mimamo_crops_to_gray": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, vp]),
+    "mimamo_crops_to_rgb": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, vp]),
+    "mimamo_resnet50_pool5_crops": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),
     "mimamo_resnet50_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.POINTER(vp)]),
     "mimamo_resnet50_destroy": (None, [vp]),
     "mimamo_resnet50_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),

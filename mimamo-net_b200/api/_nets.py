@@ -72,6 +72,23 @@ class NativeResNet50(_Handle):
         return out
 
 
+    def pool5_crops(self, preproc, crops):
+        """crops (bs,S,S,3) uint8 CUDA (OpenFace face crops) -> (bs,2048) float32 CUDA; the
+        Resize/CenterCrop/mean transform runs on the device and feeds conv1 directly."""
+        assert crops.is_cuda and crops.dtype == torch.uint8 and crops.dim() == 4 and crops.shape[-1] == 3, \
+            'expected a uint8 CUDA batch of shape (bs,S,S,3)'
+        crops = crops.contiguous()
+        bs = crops.shape[0]
+        out = torch.empty((bs, 2048), dtype=torch.float32, device=crops.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_resnet50_workspace_bytes(self.handle, bs, ctypes.byref(need)))
+        ws = self.workspace(need.value, crops.device)
+        _native.check(lib.mimamo_resnet50_pool5_crops(self.handle, preproc.handle, _native.dptr(crops), bs, _native.dptr(out),
+                                                      _native.dptr(ws), ws.numel(), _native.stream_ptr(crops.device)))
+        return out
+
+
 class NativeHead(_Handle):
     _destroy = 'mimamo_head_destroy'
 

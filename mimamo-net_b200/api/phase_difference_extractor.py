@@ -105,6 +105,29 @@ class Phase_Difference_Extractor(object):
                                            _native.dptr(ws), ws.numel(), _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
+    def phase_difference_indexed(self, frames, window_index):
+        """Clip variant of phase_difference: frames (n, W, H) are transformed
+        once each; window_index (n_windows, T) int32 names the frames of every window (the clamp rule
+        of api/sampler/snippet_sampler.py:144-152).  Returns per level (n_windows, nbands, T-1, c, c),
+        bit-identical to phase_difference(frames[window_index])."""
+        n, W, H = frames.size()
+        n_windows, T = window_index.size()
+        assert window_index.dtype == torch.int32 and window_index.device == frames.device
+        plan, _, _, frames = self._prepare(frames.view(n, 1, W, H), True)
+        outs = [torch.empty((n_windows, self.nbands, T - 1, c, c), dtype=torch.float32, device=frames.device)
+                for c in plan.crops]
+        if n_windows == 0 or T < 2:
+            return outs[0] if isinstance(self.extract_level, int) else outs
+        window_index = window_index.contiguous()
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_pyr_phase_indexed_workspace_bytes(plan.handle, n, n_windows, T, ctypes.byref(need)))
+        ws = torch.empty((max(need.value, 8),), dtype=torch.uint8, device=frames.device)
+        _native.check(lib.mimamo_pyr_phase_indexed(plan.handle, _native.dptr(frames), n, _native.dptr(window_index),
+                                                   n_windows, T, _native.ptr_array(outs), _native.dptr(ws), ws.numel(),
+                                                   _native.stream_ptr(frames.device)))
+        return outs[0] if isinstance(self.extract_level, int) else outs
+
     def show_3D_subplots(self, data, title, first_k_frames=None):
         raise NotImplementedError('visualisation is out of scope (the reference method uses undefined '
                                   'plt/cm names, api/phase_difference_extractor.py:136-152)')

@@ -56,6 +56,11 @@ class Resnet50_Extractor(object):
         """Device-resident variant of get_vec: float32 CUDA in, (bs,2048) float32 CUDA out."""
         return self.model.pool5(image)
 
+    def features_from_crops(self, crops, preprocessor):
+        """(bs,S,S,3) uint8 CUDA face crops -> (bs,2048) float32 CUDA: `self.transform` (Resize 256 ->
+        CenterCrop 224 -> ToTensor -> x255 -> Normalize) runs on the device, bit-exact with PIL."""
+        return self.model.pool5_crops(preprocessor, crops)
+
     def get_vec(self, image):
         """(bs,3,224,224) -> relu(pool5) as a CPU tensor, like the reference's hook-to-CPU (:74-83),
         including its .squeeze() (bs == 1 collapses the batch dim)."""

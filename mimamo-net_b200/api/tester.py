@@ -61,6 +61,9 @@ class Tester(object):
         self.model.to(get_device())
         self.model.eval()
         self.label_name = ['valence', 'arousal']
+        self.save_size = save_size
+        self._crop_preprocessor = None
+        self._window_index = {}
 
     # ------------------------------------------------------------------ reference surface
     def test(self, input_video):
@@ -171,6 +174,51 @@ class Tester(object):
                 if k + 2 < len(spans):
                     issue(k + 2)
             out = self.model([phase_0, phase_1], feats.view(b, f, 2048))
+        return out.cpu() if to_host else out
+
+
+    # ------------------------------------------------------------------ B200 crop path (uint8 in)
+    def crop_preprocessor(self):
+        if self._crop_preprocessor is None:
+            from utils.crop_preprocessor import Crop_Preprocessor
+            meta = self.resnet50_extractor.meta
+            self._crop_preprocessor = Crop_Preprocessor(self.save_size, self.phase_size, 256, meta['imageSize'][0],
+                                                        meta['mean'])
+        return self._crop_preprocessor
+
+    def clip_window_index(self, n_clips, n_frames, device):
+        """(n_clips*n_frames, num_phase+1) int32: frame ids of every window, each clip being its own
+        video for the clamp rule (api/sampler/snippet_sampler.py:144-152)."""
+        key = (n_clips, n_frames, str(device))
+        if key not in self._window_index:
+            from sampler.snippet_sampler import window_index
+            idx = window_index(0, n_frames, n_frames, self.num_phase)                    # (F, T)
+            idx = idx[None, :, :] + (torch.arange(n_clips) * n_frames)[:, None, None]
+            self._window_index[key] = idx.reshape(n_clips * n_frames, -1).to(device=device, dtype=torch.int32)
+        return self._window_index[key]
+
+    def infer_crops(self, crops):
+        """crops (B, F, S, S, 3) uint8 on the GPU: B clips of F aligned face crops as OpenFace writes them
+        (112x112 RGB).  Everything the reference's samplers do on the host with PIL -- convert('L'),
+        LANCZOS 48x48, /255, the 13-frame clamp windows, Resize 256 / CenterCrop 224 / mean -- runs on
+        the device, bit-exact; each distinct frame goes through the pyramid once.  Returns (B, F, 2)
+        = [valence, arousal], one GRU sequence of length B like one reference forward with batch B."""
+        with torch.no_grad():
+            b, f = crops.shape[0], crops.shape[1]
+            pre = self.crop_preprocessor()
+            flat = crops.reshape(b * f, crops.shape[2], crops.shape[3], crops.shape[4])
+            gray = pre.gray(flat)                                                       # (B*F, 48, 48)
+            idx = self.clip_window_index(b, f, crops.device)
+            diffs = self.phase_difference_extractor.phase_difference_indexed(gray, idx)
+            phase_0, phase_1 = [d.view(b, f, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+            feats = self.resnet50_extractor.features_from_crops(flat, pre).view(b, f, 2048)
+            return self.model([phase_0, phase_1], feats)
+
+    def infer_crops_host(self, crops, to_host=True):
+        """infer_crops from a HOST uint8 tensor (pinned for an asynchronous copy): 37.6 KB per frame cross
+        PCIe instead of the 722 KB of fp32 windows + RGB the reference's DataLoader ships."""
+        device = get_device()
+        out = self.infer_crops(crops.to(device, non_blocking=True))
         return out.cpu() if to_host else out
 
 

@@ -52,7 +52,7 @@ __device__ __forceinline__ float unwrap_correction(float dd) {
 
 __global__ void __launch_bounds__(kTailThreads)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
-                  const TailGeom g, const int* __restrict__ root, int nb) {
+                  const TailGeom g, const int* __restrict__ root, int nb, int coeff_T) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp;
   const int n_in = rin * cin, n_out = trp * tcp;
@@ -93,8 +93,10 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
   for (int t = 0; t < g.T; ++t) {
     long long slot = ((size_t)map * g.T + t);
     if (root != nullptr) {
+      // coefficients are laid out [frame / coeff_T][band][frame % coeff_T] (coeff_T = T for window
+      // batches, 1 for the per-frame layout of the indexed clip path)
       const int r = root[win * g.T + t];
-      slot = ((long long)(r / g.T) * nb + band) * g.T + (r % g.T);
+      slot = ((long long)(r / coeff_T) * nb + band) * coeff_T + (r % coeff_T);
     }
     const float2* src = reinterpret_cast<const float2*>(coeff) + (size_t)slot * plane;
     // (A) phase, magnitude, unwrap over time; loads are issued four at a time for memory-level parallelism
@@ -255,7 +257,7 @@ static int tail_setup() {
 
 int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, float* out,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const int* root = nullptr,
-                         int nb = 1) {
+                         int nb = 1, int coeff_T = 0) {
   MM_REQUIRE(coeff && out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "phase_extract needs T >= 2 frames and a non-empty map");
   if (n_maps == 0) return MIMAMO_OK;
@@ -269,7 +271,7 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
   const int threads = g.tile_r * g.tile_c >= 1600 ? kTailThreads : (g.tile_r * g.tile_c >= 400 ? 256 : 128);   // small maps: fewer idle threads per barrier
-  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb);
+  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
     const long long plane = (long long)rows * cols;
@@ -408,6 +410,62 @@ extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames
   for (int i = 0; i < nl; ++i) {
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
                               workspace_bytes - toff - 2 * align_up((size_t)n_frames * sizeof(int), 256), st, root, nb);
+    if (rc) return rc;
+  }
+  return MIMAMO_OK;
+}
+
+// ---- clip path: distinct frames + a window index ---------------------
+// frames f32[n_frames,H,H] are transformed ONCE each; window w, slot t reads the coefficients of frame
+// window_index[w*T + t] (the clamp rule of api/sampler/snippet_sampler.py:144-152, built by the
+// caller).  Same kernels as mimamo_pyr_phase, so results are bit-identical to materialising the
+// windows, without the 13x window copy or the frame comparison.
+static int indexed_layout(const mimamo_pyr_plan* plan, int64_t n_frames, int64_t n_windows, int T, size_t* coeff_off,
+                          size_t* tail_off, size_t* total, int* n_levels, int* nb, int* crops) {
+  mimamo_pyr_plan_levels(plan, n_levels, nb, crops);
+  size_t cur = 0, tail_need = 0;
+  for (int i = 0; i < *n_levels; ++i) {
+    coeff_off[i] = cur;
+    cur += align_up((size_t)n_frames * *nb * crops[i] * crops[i] * 2 * sizeof(float), 256);
+    size_t b = 0;
+    mimamo_phase_extract_workspace_bytes(n_windows * *nb, T, crops[i], crops[i], &b);
+    tail_need = tail_need > b ? tail_need : b;
+  }
+  *tail_off = cur;
+  size_t pyr_ws = 0;
+  mimamo_pyr_build_workspace_bytes(plan, n_frames, 1, &pyr_ws);
+  if (pyr_ws > tail_need) tail_need = pyr_ws;
+  *total = cur + align_up(tail_need, 256);
+  return MIMAMO_OK;
+}
+
+extern "C" int mimamo_pyr_phase_indexed_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_frames, int64_t n_windows,
+                                                        int32_t T, size_t* bytes_out) {
+  MM_REQUIRE(plan && bytes_out && n_frames >= 0 && n_windows >= 0 && T >= 2, MIMAMO_E_VALUE, "bad arguments");
+  size_t coff[MIMAMO_MAX_LEVELS], toff;
+  int nl, nb, crops[MIMAMO_MAX_LEVELS];
+  return indexed_layout(plan, n_frames, n_windows, T, coff, &toff, bytes_out, &nl, &nb, crops);
+}
+
+extern "C" int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float* frames, int64_t n_frames,
+                                        const int32_t* window_index, int64_t n_windows, int32_t T, float* const* out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  MM_REQUIRE(plan && out && n_frames >= 0 && n_windows >= 0 && T >= 2, MIMAMO_E_VALUE, "bad arguments");
+  if (n_windows == 0) return MIMAMO_OK;
+  MM_REQUIRE(frames && window_index && n_frames >= 1, MIMAMO_E_VALUE, "windows need at least one frame");
+  size_t coff[MIMAMO_MAX_LEVELS], toff, total;
+  int nl, nb, crops[MIMAMO_MAX_LEVELS];
+  indexed_layout(plan, n_frames, n_windows, T, coff, &toff, &total, &nl, &nb, crops);
+  MM_REQUIRE(workspace && workspace_bytes >= total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", total);
+  MM_REQUIRE(n_frames < (1ll << 31) && n_windows * T < (1ll << 31), MIMAMO_E_VALUE, "too many frames for one call");
+  float* cptr[MIMAMO_MAX_LEVELS];
+  for (int i = 0; i < nl; ++i) cptr[i] = reinterpret_cast<float*>((char*)workspace + coff[i]);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pyr_build_launch(plan, frames, n_frames, 1, cptr, nullptr, (char*)workspace + toff, total - toff, st);
+  if (rc) return rc;
+  for (int i = 0; i < nl; ++i) {
+    rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
+                              total - toff, st, window_index, nb, 1);
     if (rc) return rc;
   }
   return MIMAMO_OK;

@@ -117,11 +117,16 @@ extern "C" int mimamo_resnet50_workspace_bytes(const mimamo_resnet50* net, int32
   return MIMAMO_OK;
 }
 
-extern "C" int mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x, int32_t batch, float* out, void* workspace,
-                                     size_t workspace_bytes, void* stream_) {
-  MM_REQUIRE(net && x && out && batch >= 0, MIMAMO_E_VALUE, "bad arguments");
-  if (batch == 0) return MIMAMO_OK;
-  cudaStream_t stream = (cudaStream_t)stream_;
+struct mimamo_preproc;
+namespace mimamo {
+int crops_rgb_launch(const mimamo_preproc* p, const uint8_t* crops, int64_t n, void* out, int mode, cudaStream_t s);
+}
+extern "C" int mimamo_preproc_geometry(const mimamo_preproc* p, int32_t* src, int32_t* gray_size, int32_t* crop);
+
+// x != nullptr: fp32 NCHW frames; otherwise uint8 face crops preprocessed on the fly (preproc.cu)
+static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mimamo_preproc* pre, const uint8_t* crops,
+                            int crop_edge, int32_t batch, float* out, void* workspace, size_t workspace_bytes,
+                            cudaStream_t stream) {
   size_t need = 0;
   mimamo_resnet50_workspace_bytes(net, batch, &need);
   MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
@@ -137,7 +142,11 @@ extern "C" int mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x,
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = batch - b0 < chunk ? batch - b0 : chunk;
     int rc;
-    if (net->use_im2col) {
+    if (crops) {
+      // resize + centre crop + mean subtraction straight into the space-to-depth'ed conv1 operand
+      rc = crops_rgb_launch(pre, crops + (size_t)b0 * crop_edge * crop_edge * 3, Bc, A0, net->elem == kBF16 ? 1 : 2, stream);
+      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, C1, 64, stream);
+    } else if (net->use_im2col) {
       rc = im2col_conv1(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
       if (!rc) rc = gemm_forward(net->conv1_im2col, A0, Bc * 12544, C1, 64, nullptr, 0, stream);
     } else {
@@ -167,4 +176,23 @@ extern "C" int mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x,
     if (rc) return rc;
   }
   return MIMAMO_OK;
+}
+
+extern "C" int mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x, int32_t batch, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+  MM_REQUIRE(net && x && out && batch >= 0, MIMAMO_E_VALUE, "bad arguments");
+  if (batch == 0) return MIMAMO_OK;
+  return resnet50_forward(net, x, nullptr, nullptr, 0, batch, out, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+// uint8 face crops [batch, S, S, 3] -> pool5: Image_Sampler's transform (api/utils/model_utils.py:26-40) runs on the
+// device, bit-exact with PIL, and feeds conv1 directly (no fp32 frame is ever materialised).
+extern "C" int mimamo_resnet50_pool5_crops(const mimamo_resnet50* net, const mimamo_preproc* pre, const uint8_t* crops,
+                                           int32_t batch, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  MM_REQUIRE(net && pre && crops && out && batch >= 0, MIMAMO_E_VALUE, "bad arguments");
+  if (batch == 0) return MIMAMO_OK;
+  int32_t src = 0, crop = 0;
+  mimamo_preproc_geometry(pre, &src, nullptr, &crop);
+  MM_REQUIRE(crop == 224, MIMAMO_E_RUNTIME, "ResNet50 needs 224x224 centre crops, the plan produces %d", crop);
+  return resnet50_forward(net, nullptr, pre, crops, src, batch, out, workspace, workspace_bytes, (cudaStream_t)stream_);
 }

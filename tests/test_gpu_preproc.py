@@ -1,0 +1,89 @@
+"""GPU parity of the uint8 face-crop path: on-device PIL-exact preprocessing, the indexed
+pyramid/phase entry and Tester.infer_crops, all through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mimamo_oracle as O
+from oracle import pil_preproc as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _crops(n, seed, size=112):
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, 256, (n, size, size, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:size, 0:size]
+    for i in range(0, n, 3):                                  # every third crop smooth, with a drifting pattern
+        c[i] = np.stack([(127 + 110 * np.sin(xx / 9.0 + 0.3 * i + ch) * np.cos(yy / 13.0)).astype(np.uint8) for ch in range(3)], -1)
+    return c
+
+
+def test_preprocessing_is_bit_exact_with_pil(cuda, golden_dir):
+    from utils.crop_preprocessor import Crop_Preprocessor
+    g = np.load(os.path.join(golden_dir, "preproc_pil.npz"))
+    pre = Crop_Preprocessor()
+    crops = torch.from_numpy(g["crops"]).to(cuda)
+    gray = pre.gray(crops).cpu().numpy()
+    rgb = pre.rgb(crops).cpu().numpy()
+    assert np.array_equal(gray, g["gray"])                    # produced by PIL itself
+    assert np.array_equal(rgb[:, :, :8, :], g["rgb_f32_rows"])  # produced by torchvision itself
+    assert np.array_equal(rgb, P.crops_to_rgb(g["crops"]))
+    more = _crops(9, 5)
+    assert np.array_equal(pre.gray(torch.from_numpy(more).to(cuda)).cpu().numpy(), P.crops_to_gray(more))
+    assert np.array_equal(pre.rgb(torch.from_numpy(more).to(cuda)).cpu().numpy(), P.crops_to_rgb(more))
+    assert pre.gray(crops[:0]).shape == (0, 48, 48)
+    with pytest.raises(ValueError):
+        pre.gray(torch.zeros(2, 100, 112, 3, dtype=torch.uint8, device=cuda))
+
+
+def test_other_crop_geometry(cuda):
+    """save_size is a Tester argument (api/tester.py:18): a 96x96 crop must resample with its own tables."""
+    from utils.crop_preprocessor import Crop_Preprocessor
+    pre = Crop_Preprocessor(save_size=96, phase_size=32)
+    c = _crops(3, 8, size=96)
+    assert np.array_equal(pre.gray(torch.from_numpy(c).to(cuda)).cpu().numpy(), P.crops_to_gray(c, 32))
+    assert np.array_equal(pre.rgb(torch.from_numpy(c).to(cuda)).cpu().numpy(), P.crops_to_rgb(c))
+
+
+def test_indexed_pyramid_matches_window_path(cuda):
+    from phase_difference_extractor import Phase_Difference_Extractor
+    from sampler.snippet_sampler import window_index
+    pde = Phase_Difference_Extractor(height=4, nbands=2, extract_level=[1, 2])
+    gen = torch.Generator().manual_seed(3)
+    frames = torch.rand(30, 48, 48, generator=gen).to(cuda)
+    idx = window_index(0, 30, 30, 12).to(cuda, torch.int32)
+    a = pde.phase_difference_indexed(frames, idx)
+    b = pde.phase_difference(frames[idx.long()])
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)
+    ref0, ref1 = O.phase_diff_output(frames.cpu()[idx.long().cpu()][None])
+    err = max((a[0].cpu().reshape(ref0.shape) - ref0).abs().max().item(), (a[1].cpu().reshape(ref1.shape) - ref1).abs().max().item())
+    print("indexed pyramid+phase vs oracle: max|err| %.3e" % err)
+    assert err < 1e-4                                         # north_star: phase maps within 1e-4 abs
+
+
+def test_infer_crops_matches_clip_path_and_oracle(cuda):
+    from tester import Tester
+    B, Fr = 2, 16
+    crops = _crops(B * Fr, 11).reshape(B, Fr, 112, 112, 3)
+    net = O.resnet_synthetic(1)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(), seed=1)
+    t = Tester(None, batch_size=B, resnet_model=net, head_state_dict=sd)
+    out = t.infer_crops(torch.from_numpy(crops).to(cuda)).cpu()
+    # the same inputs prepared on the host exactly like the reference's samplers do
+    gray = torch.from_numpy(P.crops_to_gray(crops.reshape(-1, 112, 112, 3))).view(B, Fr, 48, 48)
+    windows = torch.stack([O.gather_windows(gray[b], 0, Fr) for b in range(B)])
+    rgb = torch.from_numpy(P.crops_to_rgb(crops.reshape(-1, 112, 112, 3)))
+    via_clips = t.infer_clips(windows.to(cuda), rgb.to(cuda)).cpu()
+    assert torch.equal(out, via_clips)                        # same bits: only where the preprocessing ran differs
+    p0, p1 = O.phase_diff_output(windows)
+    with torch.no_grad():
+        ref = O.head_forward(sd, p0, p1, O.resnet_pool5(net, rgb).view(B, Fr, 2048))
+    err = (out - ref).abs().max().item()
+    print("crop path end-to-end (bf16 ResNet): valence/arousal max|err| %.3e" % err)
+    assert out.shape == (B, Fr, 2) and err < 3e-2
+    host = t.infer_crops_host(torch.from_numpy(crops).pin_memory())
+    assert torch.equal(host, out)
