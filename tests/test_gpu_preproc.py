@@ -21,8 +21,10 @@ def _crops(n, seed, size=112):
     return c
 
 
-def test_preprocessing_is_bit_exact_with_pil(cuda, golden_dir):
+@pytest.mark.parametrize("generic", ["0", "1"])          # 3-tap word-wise RGB kernel / generic any-tap kernel
+def test_preprocessing_is_bit_exact_with_pil(cuda, golden_dir, generic, monkeypatch):
     from utils.crop_preprocessor import Crop_Preprocessor
+    monkeypatch.setenv("MIMAMO_PREPROC_GENERIC", generic)
     g = np.load(os.path.join(golden_dir, "preproc_pil.npz"))
     pre = Crop_Preprocessor()
     crops = torch.from_numpy(g["crops"]).to(cuda)
