@@ -232,7 +232,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
 template <int BLOCK_N, bool HAS_RES>
 struct GemmCfg {
   static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kEpiBytes = kEpiWarps * 32 * 128;                       // TMEM -> coalesced-layout staging
+  static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;                        // 16-bit [128][BLOCK_N] TMA-store staging
   static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
@@ -263,25 +263,51 @@ __device__ __forceinline__ int row_pixel(const ConvParams& p, int m_tile, int ro
   return (row < p.a_rows && n < p.Nimg && h < p.Ho && w < p.Wo) ? (n * p.Ho + h) * p.Wo + w : -1;
 }
 
-// Epilogue warps (shared by both kernels): TMEM -> registers (thread = output row) -> XOR-swizzled
-// fp32 staging in shared memory -> (lane = 8 channels of 8 rows) so that every global access is a
-// coalesced 16-byte vector.  The residual is prefetched by per-lane cp.async into a ring kResDepth
-// chunks deep that runs ahead ACROSS tiles (each lane later consumes exactly the bytes it fetched).
+// ---- TMA store / async-proxy helpers ----
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void tma_store_2d(uint64_t map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(uint64_t map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue warps (shared by all three kernels).  ncu on the first versions (profiles/gemm_r1_ncu_summary_v2.txt)
+// showed the 1x1 layers bound by the epilogue's shared-memory instruction queue (mio_throttle): TMEM -> fp32
+// staging -> coalesced re-read -> 16-byte global stores moved every output through the LSU three times.
+// Now each thread keeps the accumulator row tcgen05.ld hands it (thread = output row, 32 columns per chunk),
+// applies folded BatchNorm / residual / ReLU in registers, packs to 16 bits and writes its 64 bytes ONCE into a
+// swizzled [128 rows][COLS] staging tile; the four warps of a column group (one per TMEM lane quarter) then hand
+// the whole tile to the TMA engine (cp.async.bulk.tensor store), which clips rows/columns outside the tensor --
+// so padded accumulator rows (partial tiles, the two extra columns of a halo line) need no predicate at all.
+// The residual is prefetched by per-lane cp.async into a ring kResDepth chunks deep that runs ahead ACROSS tiles,
+// written in the same swizzled row layout so that thread = row reads it back conflict-free.
 template <int BLOCK_N, bool BF16, bool HAS_RES>
-__device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, int lane, uint8_t* sEpi, uint8_t* sRes,
-                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
+                                               uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
                                                int num_tiles) {
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
-    constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per TMEM quarter (64-wide tiles: 2)
+    constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per tile (64-wide tiles: 2)
     const int half = ew >> 2;                                 // which column group this warp owns
-    constexpr int COLS = BLOCK_N / PARTS;                     // columns per epilogue warp
+    constexpr int COLS = BLOCK_N / PARTS;                     // columns per column group: 32 or 64
     constexpr int CPW = COLS / 32;                            // 32-column chunks per warp per tile
+    constexpr int ROW_BYTES = COLS * 2;                       // staging row: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
     if (half < PARTS) {
-    const uint32_t stage_u32 = smem_u32(sEpi + ew * (32 * 128));
+    const int row = quarter * 32 + lane;                      // accumulator row of this thread
+    const uint32_t stage_u32 = smem_u32(sEpi + half * (128 * ROW_BYTES));
+    const uint32_t my_row_u32 = stage_u32 + row * ROW_BYTES;
+    const uint32_t swz = ROW_BYTES == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);   // XOR on the 16-byte chunk index
     const uint32_t res_u32 = smem_u32(sRes + ew * (kResDepth * 2048));
-    const int sub_row = lane >> 2, pair = lane & 3;           // phase 2: row (it*8 + sub_row), channels pair*8..+8
+    const int sub_row = lane >> 2, pair = lane & 3;           // residual fetch: row (it*8 + sub_row), 16-byte piece `pair`
     const uint16_t* res_base = reinterpret_cast<const uint16_t*>(p.residual);
+    const bool issuer = quarter == 0 && lane == 0;            // one thread per column group issues the TMA store
+    const uint64_t map_out = reinterpret_cast<uint64_t>(tmOut);
+    const int bar_id = 1 + half;
 
     auto issue_residual = [&](int q) {                        // chunk q of this warp's flattened (tile, chunk) list
       if (HAS_RES) {
@@ -291,9 +317,10 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
           const int ch = n_tile * BLOCK_N + half * COLS + (q % CPW) * 32 + pair * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            const int rp = row_pixel(p, m_tile, quarter * 32 + it * 8 + sub_row);
+            const int r = it * 8 + sub_row;
+            const int rp = row_pixel(p, m_tile, quarter * 32 + r);
             if (rp >= 0) {
-              const uint32_t dst = res_u32 + (q % kResDepth) * 2048 + (it * 32 + lane) * 16;
+              const uint32_t dst = res_u32 + (q % kResDepth) * 2048 + r * 64 + ((pair ^ ((r >> 1) & 3)) << 4);
               asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(res_base + (size_t)rp * p.ld_res + ch) : "memory");
             }
           }
@@ -309,84 +336,87 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const int pix = row_pixel(p, m_tile, quarter * 32 + lane);
       const int n0 = n_tile * BLOCK_N + half * COLS;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      // the staging tile is free once the previous tile's TMA store has read it
+      if (issuer) tma_store_wait_read();
+      named_bar_sync(bar_id, 128);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
         uint32_t v[32];
         tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        uint32_t rw[16];
+        if (HAS_RES) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(kResDepth - 1) : "memory");
+          __syncwarp();                                        // every lane's pieces of the chunk have landed
+          const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4 * j]), "=r"(rw[4 * j + 1]), "=r"(rw[4 * j + 2]), "=r"(rw[4 * j + 3])
+                         : "r"(src + ((j ^ ((lane >> 1) & 3)) << 4)));
+        }
         tmem_ld_wait();
+        const float4* sc = reinterpret_cast<const float4*>(p.scale + n0 + c0);      // warp-uniform addresses: broadcast loads
+        const float4* sh = reinterpret_cast<const float4*>(p.shift + n0 + c0);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {                         // 8 chunks of 4 fp32; physical chunk = g ^ (row & 7)
-          const uint32_t addr = stage_u32 + lane * 128 + ((g ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * g]), "r"(v[4 * g + 1]),
-                       "r"(v[4 * g + 2]), "r"(v[4 * g + 3]) : "memory");
-        }
-        if (HAS_RES) asm volatile("cp.async.wait_group %0;" ::"n"(kResDepth - 1) : "memory");
-        __syncwarp();
-        const int ch = n0 + c0 + pair * 8;
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + ch)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + ch + 4));
-        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + ch)), t1 = __ldg(reinterpret_cast<const float4*>(p.shift + ch + 4));
-        // all shared-memory reads of the chunk are issued before any is consumed (ILP: the epilogue
-        // is latency-bound, not bandwidth-bound)
-        int rps[4];
-        float4 va[4], vb[4];
-        uint32_t rw[4][4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 8 + sub_row;
-          rps[it] = __shfl_sync(0xffffffffu, pix, r);
-          const uint32_t a0 = stage_u32 + r * 128 + (((2 * pair) ^ (r & 7)) << 4);
-          const uint32_t a1 = stage_u32 + r * 128 + (((2 * pair + 1) ^ (r & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(va[it].x), "=f"(va[it].y), "=f"(va[it].z), "=f"(va[it].w) : "r"(a0));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vb[it].x), "=f"(vb[it].y), "=f"(vb[it].z), "=f"(vb[it].w) : "r"(a1));
+        for (int g = 0; g < 4; ++g) {                          // 8 columns = one 16-byte chunk of the 16-bit row
+          const float4 s0 = __ldg(sc + 2 * g), s1 = __ldg(sc + 2 * g + 1), t0 = __ldg(sh + 2 * g), t1 = __ldg(sh + 2 * g + 1);
+          float o[8] = {__uint_as_float(v[8 * g]) * s0.x + t0.x, __uint_as_float(v[8 * g + 1]) * s0.y + t0.y,
+                        __uint_as_float(v[8 * g + 2]) * s0.z + t0.z, __uint_as_float(v[8 * g + 3]) * s0.w + t0.w,
+                        __uint_as_float(v[8 * g + 4]) * s1.x + t1.x, __uint_as_float(v[8 * g + 5]) * s1.y + t1.y,
+                        __uint_as_float(v[8 * g + 6]) * s1.z + t1.z, __uint_as_float(v[8 * g + 7]) * s1.w + t1.w};
           if (HAS_RES) {
-            const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + (it * 32 + lane) * 16;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[it][0]), "=r"(rw[it][1]), "=r"(rw[it][2]), "=r"(rw[it][3]) : "r"(src));
-          }
-        }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rp = rps[it];
-          const float4 a = va[it], b = vb[it];
-          if (rp >= 0) {
-            float o[8] = {a.x * s0.x + t0.x, a.y * s0.y + t0.y, a.z * s0.z + t0.z, a.w * s0.w + t0.w,
-                          b.x * s1.x + t1.x, b.y * s1.y + t1.y, b.z * s1.z + t1.z, b.w * s1.w + t1.w};
-            if (HAS_RES) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack2<BF16>(rw[it][j]);
-                o[2 * j] += f.x; o[2 * j + 1] += f.y;
-              }
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<BF16>(rw[4 * g + j]);
+              o[2 * j] += f.x; o[2 * j + 1] += f.y;
             }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            const uint4 pk = make_uint4(pack2<BF16>(o[0], o[1]), pack2<BF16>(o[2], o[3]), pack2<BF16>(o[4], o[5]),
-                                        pack2<BF16>(o[6], o[7]));
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + (size_t)rp * p.ldc + ch) = pk;
           }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          const uint32_t chunk = (uint32_t)(c0 / 8 + g);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_u32 + ((chunk ^ swz) << 4)), "r"(pack2<BF16>(o[0], o[1])),
+                       "r"(pack2<BF16>(o[2], o[3])), "r"(pack2<BF16>(o[4], o[5])), "r"(pack2<BF16>(o[6], o[7])) : "memory");
         }
-        __syncwarp();
-        issue_residual(qc + kResDepth);                       // refill the ring slot just consumed
+        if (HAS_RES) {
+          __syncwarp();                                        // all lanes have read the ring slot
+          issue_residual(qc + kResDepth);                      // refill it
+        }
       }
+      // accumulator fully read: hand the TMEM buffer back before the store is even issued
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA engine
+      named_bar_sync(bar_id, 128);
+      if (issuer) {
+        if (p.mode == 0) {
+          tma_store_2d(map_out, stage_u32, n0, m_tile * kBlockM);
+        } else if (p.mode == 2) {
+          const int n_img = m_tile / p.tiles_h, th = m_tile - n_img * p.tiles_h;
+          tma_store_4d(map_out, stage_u32, n0, 0, th * p.bh, n_img);
+        } else {
+          const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
+          const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
+          tma_store_4d(map_out, stage_u32, n0, tw * p.bw, th * p.bh, tn * p.bn);
+        }
+        tma_store_commit();
+      }
     }
     if (HAS_RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (issuer) tma_store_wait_all();
     }
 }
 
 template <int BLOCK_N, bool BF16, bool HAS_RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
   using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -405,6 +435,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
     fence_barrier_init();
@@ -497,7 +528,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, HAS_RES>(p, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, HAS_RES>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -526,7 +557,7 @@ constexpr int kHaloAStages = 2;
 template <int BLOCK_N>
 struct HaloCfg {
   static constexpr int kBStageBytes = 3 * BLOCK_N * kBlockK * 2;          // the three taps of one kernel row
-  static constexpr int kEpiBytes = kEpiWarps * 32 * 128;
+  static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
   static constexpr int kBStages = (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes > 6
                                       ? 6 : (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
@@ -537,7 +568,7 @@ struct HaloCfg {
 template <int BLOCK_N, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
   using Cfg = HaloCfg<BLOCK_N>;
   constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
@@ -557,6 +588,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&full_b[i], 1); mbar_init(&empty_b[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
@@ -657,7 +689,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false>(p, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, false>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -679,7 +711,8 @@ constexpr int kLineABytes = 16384;
 constexpr int kLineAStages = 6;
 constexpr int kLineWBytes = 32768;
 constexpr uint32_t kDescHi32 = 16u | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
-constexpr int kLineSmemBytes = kLineWBytes + kLineAStages * kLineABytes + kEpiWarps * 32 * 128 + 512 + 1024;
+constexpr int kLineEpiBytes = kBlockM * 64 * 2;
+constexpr int kLineSmemBytes = kLineWBytes + kLineAStages * kLineABytes + kLineEpiBytes + 512 + 1024;
 
 __device__ __forceinline__ void umma_one(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
                                          uint32_t hi) {
@@ -698,14 +731,14 @@ __device__ __forceinline__ void umma_one(uint32_t d_tmem, uint32_t a_lo, uint32_
 template <bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
   constexpr int SA = kLineAStages, BLOCK_N = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sA = smem + kLineWBytes;
   uint8_t* sEpi = sA + SA * kLineABytes;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * 32 * 128);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sEpi + kLineEpiBytes);
   uint64_t* empty_a = full_a + SA;
   uint64_t* w_full = empty_a + SA;
   uint64_t* tmem_full = w_full + 1;
@@ -715,6 +748,7 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * 2); }
@@ -777,7 +811,7 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++sa == SA) { sa = 0; pa ^= 1; }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false>(p, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, false>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -848,7 +882,7 @@ static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
 
 template <int BLOCK_N, bool BF16, bool HAS_RES>
-static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
+static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -870,16 +904,16 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvPara
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
-  conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
+  conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
 }
 
 template <int BLOCK_N>
-static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
-  if (bf) return res ? launch_cfg<BLOCK_N, true, true>(a, b, p, s) : launch_cfg<BLOCK_N, true, false>(a, b, p, s);
-  return res ? launch_cfg<BLOCK_N, false, true>(a, b, p, s) : launch_cfg<BLOCK_N, false, false>(a, b, p, s);
+static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
+  if (bf) return res ? launch_cfg<BLOCK_N, true, true>(a, b, o, p, s) : launch_cfg<BLOCK_N, true, false>(a, b, o, p, s);
+  return res ? launch_cfg<BLOCK_N, false, true>(a, b, o, p, s) : launch_cfg<BLOCK_N, false, false>(a, b, o, p, s);
 }
 
 // BLOCK_N actually launched: residual layers use at most 128 columns (the residual ring takes the
@@ -893,19 +927,38 @@ static int effective_block_n(const ConvLayer& L, bool has_res) {
   return (has_res && L.block_n > res_bn) ? res_bn : L.block_n;
 }
 
-static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
+// Output tensor map for the epilogue's TMA store: the 16-bit NHWC output viewed as [rows][Cout] (flat) or
+// [B][Ho][Wo][Cout] (spatial), one box = one column group (32 or 64 channels) of one tile's pixels.
+static int out_cols(int block_n) { return block_n >= 256 ? 64 : 32; }
+static int out_map_flat(CUtensorMap* map, ElemType elem, void* out, int ldc, int cout, long long rows, int block_n) {
+  const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)rows};
+  const uint64_t strides[1] = {(uint64_t)ldc * 2};
+  const uint32_t box[2] = {(uint32_t)out_cols(block_n), (uint32_t)kBlockM};
+  const uint32_t es[2] = {1, 1};
+  return encode_map(map, elem, 2, out, dims, strides, box, es, out_cols(block_n) == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+static int out_map_spatial(CUtensorMap* map, ElemType elem, void* out, int ldc, int cout, int Wo, int Ho, int B, int bw, int bh,
+                           int bn, int block_n) {
+  const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ldc * 2, (uint64_t)Wo * ldc * 2, (uint64_t)Ho * Wo * ldc * 2};
+  const uint32_t box[4] = {(uint32_t)out_cols(block_n), (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  const uint32_t es[4] = {1, 1, 1, 1};
+  return encode_map(map, elem, 4, out, dims, strides, box, es, out_cols(block_n) == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
   const bool bf = L.elem == kBF16, res = p.residual != nullptr;
   switch (effective_block_n(L, res)) {
-    case 64:  return launch_n<64>(bf, res, a, b, p, s);
-    case 128: return launch_n<128>(bf, res, a, b, p, s);
-    case 256: return launch_n<256>(bf, res, a, b, p, s);
+    case 64:  return launch_n<64>(bf, res, a, b, o, p, s);
+    case 128: return launch_n<128>(bf, res, a, b, o, p, s);
+    case 256: return launch_n<256>(bf, res, a, b, o, p, s);
   }
   set_error("unsupported BLOCK_N %d", L.block_n);
   return MIMAMO_E_RUNTIME;
 }
 
 template <int BLOCK_N, bool BF16>
-static int launch_halo_cfg(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t stream) {
+static int launch_halo_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -927,7 +980,7 @@ static int launch_halo_cfg(const CUtensorMap& a, const CUtensorMap& b, const Con
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
-  conv3x3_halo_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, p);
+  conv3x3_halo_kernel<BLOCK_N, BF16><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
@@ -1011,7 +1064,10 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   if (rc) return rc;
   p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
-  return launch(L, ma, mb, p, stream);
+  CUtensorMap mo;
+  rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr));
+  if (rc) return rc;
+  return launch(L, ma, mb, mo, p, stream);
 }
 
 int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc, const void* residual,
@@ -1061,8 +1117,11 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
         p.resident_w = (p.cin_blocks == 1 && p.n_tiles == 1 && !(e && e[0] == '0')) ? 1 : 0;
       }
       const bool bf = L.elem == kBF16;
-      if (L.block_n == 64) return bf ? launch_halo_cfg<64, true>(ma, mb, p, stream) : launch_halo_cfg<64, false>(ma, mb, p, stream);
-      return bf ? launch_halo_cfg<128, true>(ma, mb, p, stream) : launch_halo_cfg<128, false>(ma, mb, p, stream);
+      CUtensorMap mo;                                          // one box = bh padded lines; the two extra columns per line fall outside Wo and are clipped
+      rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, line, bh, 1, bn_cols);
+      if (rc) return rc;
+      if (L.block_n == 64) return bf ? launch_halo_cfg<64, true>(ma, mb, mo, p, stream) : launch_halo_cfg<64, false>(ma, mb, mo, p, stream);
+      return bf ? launch_halo_cfg<128, true>(ma, mb, mo, p, stream) : launch_halo_cfg<128, false>(ma, mb, mo, p, stream);
     }
   }
   // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows
@@ -1098,7 +1157,10 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.tiles_h = (Ho + best_bh - 1) / best_bh;
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
-  return launch(L, ma, mb, p, stream);
+  CUtensorMap mo;
+  rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, best_bw, best_bh, best_bn, effective_block_n(L, residual != nullptr));
+  if (rc) return rc;
+  return launch(L, ma, mb, mo, p, stream);
 }
 
 // conv1_7x7_s2 without an im2col buffer.  The input is space-to-depth'ed once (2x2 -> 12 (+4 zero)
@@ -1131,7 +1193,10 @@ static int conv1_s2d_forward_windows(const ConvLayer& L, const void* s2d, int B,
   p.tiles_w = Wo / bw; p.tiles_h = Ho / bh;
   p.a_rows = bw * bh;
   p.m_tiles = p.tiles_w * p.tiles_h * B;
-  return launch(L, ma, mb, p, stream);
+  CUtensorMap mo;
+  rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, bw, bh, 1, 64);
+  if (rc) return rc;
+  return launch(L, ma, mb, mo, p, stream);
 }
 
 
@@ -1190,8 +1255,13 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * 64.0 * 256.0;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
-  if (bf) conv1_line_kernel<true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, p);
-  else conv1_line_kernel<false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, p);
+  CUtensorMap mo;                                              // one box = one 115-pixel padded line; columns >= 112 are clipped
+  {
+    int rc = out_map_spatial(&mo, L.elem, out, ldc, 64, Wo, Ho, B, S2D, 1, 1, 64);
+    if (rc) return rc;
+  }
+  if (bf) conv1_line_kernel<true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+  else conv1_line_kernel<false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
