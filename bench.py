@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="print per-launch GEMM times to stderr")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up, device-timed leg only")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -206,6 +207,13 @@ def main():
     import ctypes
     gemm_ms, gemm_n, issued = ctypes.c_double(0), ctypes.c_uint64(0), ctypes.c_double(0)
     lib.mimamo_profile_gemm_read(ctypes.byref(gemm_ms), ctypes.byref(gemm_n), ctypes.byref(issued))
+    if args.layers:                                             # per-launch CUDA-event times of the GEMM kernels (steady state, real clocks)
+        buf = (ctypes.c_float * 4096)()
+        n = lib.mimamo_profile_gemm_launches(buf, 4096)
+        per = n // args.steps
+        avg = [sum(buf[k * per + i] for k in range(args.steps)) / args.steps * 1e3 for i in range(per)]
+        print("gemm launches per step: %d; us per launch (avg over %d steps):" % (per, args.steps), file=sys.stderr)
+        print(" ".join("%.0f" % v for v in avg), file=sys.stderr)
     lib.mimamo_profile_gemm(0)
     # per-stage device time (same inputs, each stage alone), reported next to the whole-step number
     def stage_ms(fn, reps=3):

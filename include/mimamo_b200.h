@@ -183,6 +183,8 @@ int  mimamo_head_forward(const mimamo_head* head, const float* phase_0, const fl
  * enable=1 resets and starts recording; read after synchronising the stream. */
 int mimamo_profile_gemm(int32_t enable);
 int mimamo_profile_gemm_read(double* total_ms, uint64_t* launches, double* issued_flops);
+/* per-launch durations in ms, launch order; returns how many were written (<= max_launches) */
+int mimamo_profile_gemm_launches(float* ms_out, int32_t max_launches);
 
 /* Test hook: one conv layer through the tcgen05 implicit-GEMM engine.
  * x bf16 NHWC [B,H,W,Cin] (Cin multiple of 8), w f32 [Cout,Cin,k,k] (torch layout),

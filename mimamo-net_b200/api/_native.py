@@ -76,6 +76,7 @@ _SIGNATURES = {
     "mimamo_profile_gemm": (ctypes.c_int, [ctypes.c_int32]),
     "mimamo_profile_gemm_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
                                                 ctypes.POINTER(ctypes.c_double)]),
+    "mimamo_profile_gemm_launches": (ctypes.c_int, [c_float_p, ctypes.c_int32]),
     "mimamo_conv_bf16": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         c_float_p, c_float_p, c_float_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]),

@@ -50,6 +50,7 @@ struct ConvParams {
   void* out;
   int ldc, ld_res;
   int relu;
+  int store_mode;            // epilogue TMA store granularity: 0 = per warp (32 rows, flat layers), 1 = per column group, 2 = whole tile
   int resident_w;            // halo kernel: the whole 3x3 weight set stays in shared memory (Cin_p == 64, 9 taps <= kBStages boxes)
 };
 
@@ -285,7 +286,9 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // the whole tile to the TMA engine (cp.async.bulk.tensor store), which clips rows/columns outside the tensor --
 // so padded accumulator rows (partial tiles, the two extra columns of a halo line) need no predicate at all.
 // The residual is prefetched by per-lane cp.async into a ring kResDepth chunks deep that runs ahead ACROSS tiles,
-// written in the same swizzled row layout so that thread = row reads it back conflict-free.
+// written in the same swizzled row layout so that thread = row reads it back conflict-free.  (Pulling the residual
+// of later tiles into L2 first -- TMA prefetch or prefetch.global.L2 -- was measured 10-15 % SLOWER: these layers
+// are bound by bytes through L2, and a prefetch moves every residual byte through it twice.)
 template <int BLOCK_N, bool BF16, bool HAS_RES>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
@@ -305,9 +308,18 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
     const uint32_t res_u32 = smem_u32(sRes + ew * (kResDepth * 2048));
     const int sub_row = lane >> 2, pair = lane & 3;           // residual fetch: row (it*8 + sub_row), 16-byte piece `pair`
     const uint16_t* res_base = reinterpret_cast<const uint16_t*>(p.residual);
-    const bool issuer = quarter == 0 && lane == 0;            // one thread per column group issues the TMA store
-    const uint64_t map_out = reinterpret_cast<uint64_t>(tmOut);
+    // Who hands finished rows to the TMA engine (measured per layer type, profiles/launches_r1_*.csv): the epilogue-
+    // bound flat 1x1 layers want the warps fully decoupled (each warp stores its own 32 rows); the tensor-bound 3x3
+    // layers run faster when the whole tile goes out behind one barrier; strided 1x1 boxes go per column group.
+    const int store_mode = p.store_mode;
+    const bool issuer = store_mode == 0 ? lane == 0 : (store_mode == 1 ? (quarter == 0 && lane == 0) : (ew == 2 && lane == 0));
     const int bar_id = 1 + half;
+    const uint64_t map_out = reinterpret_cast<uint64_t>(tmOut);
+    auto sync_store_group = [&]() {
+      if (store_mode == 0) __syncwarp();
+      else if (store_mode == 1) named_bar_sync(bar_id, 128);
+      else named_bar_sync(1, PARTS * 128);
+    };
 
     auto issue_residual = [&](int q) {                        // chunk q of this warp's flattened (tile, chunk) list
       if (HAS_RES) {
@@ -341,7 +353,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       tc_fence_after();
       // the staging tile is free once the previous tile's TMA store has read it
       if (issuer) tma_store_wait_read();
-      named_bar_sync(bar_id, 128);
+      sync_store_group();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
@@ -393,17 +405,26 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA engine
-      named_bar_sync(bar_id, 128);
+      sync_store_group();
       if (issuer) {
-        if (p.mode == 0) {
-          tma_store_2d(map_out, stage_u32, n0, m_tile * kBlockM);
-        } else if (p.mode == 2) {
-          const int n_img = m_tile / p.tiles_h, th = m_tile - n_img * p.tiles_h;
-          tma_store_4d(map_out, stage_u32, n0, 0, th * p.bh, n_img);
+        if (store_mode == 0) {                                 // flat layer: this warp's 32 rows
+          tma_store_2d(map_out, stage_u32 + quarter * (32 * ROW_BYTES), n0, m_tile * kBlockM + quarter * 32);
         } else {
-          const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
-          const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
-          tma_store_4d(map_out, stage_u32, n0, tw * p.bw, th * p.bh, tn * p.bn);
+          const int g0 = store_mode == 1 ? half : 0, g1 = store_mode == 1 ? half + 1 : PARTS;
+          for (int g = g0; g < g1; ++g) {
+            const uint32_t src = smem_u32(sEpi) + g * (128 * ROW_BYTES);
+            const int nc = n_tile * BLOCK_N + g * COLS;
+            if (p.mode == 0) {
+              tma_store_2d(map_out, src, nc, m_tile * kBlockM);
+            } else if (p.mode == 2) {
+              const int n_img = m_tile / p.tiles_h, th = m_tile - n_img * p.tiles_h;
+              tma_store_4d(map_out, src, nc, 0, th * p.bh, n_img);
+            } else {
+              const int tw = m_tile % p.tiles_w, rest = m_tile / p.tiles_w;
+              const int th = rest % p.tiles_h, tn = rest / p.tiles_h;
+              tma_store_4d(map_out, src, nc, tw * p.bw, th * p.bh, tn * p.bn);
+            }
+          }
         }
         tma_store_commit();
       }
@@ -552,17 +573,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // and weights use separate rings (one patch feeds nine weight boxes).
 // ---------------------------------------------------------------------------------------
 constexpr int kHaloABytes = 32768;            // (bh+2)*(W+2) <= 256 patch pixels x 128 B
-constexpr int kHaloAStages = 2;
 
 template <int BLOCK_N>
 struct HaloCfg {
+  // Patch ring depth: with two stages the next tile's patch load only overlapped one tile's MMAs (~0.6 us for
+  // 64 -> 64), shorter than the load latency, so the 64-wide layer sat at 1.6 us per tile; four stages (the
+  // resident weights leave the room) keep three patches in flight.
+  static constexpr int kAStages = BLOCK_N <= 64 ? 4 : 3;
   static constexpr int kBStageBytes = 3 * BLOCK_N * kBlockK * 2;          // the three taps of one kernel row
   static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
-  static constexpr int kBStages = (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes > 6
-                                      ? 6 : (232448 - 1024 - 512 - kEpiBytes - kHaloAStages * kHaloABytes) / kBStageBytes;
+  static constexpr int kRoom = (232448 - 1024 - 512 - kEpiBytes - kAStages * kHaloABytes) / kBStageBytes;
+  static constexpr int kBStages = kRoom > 6 ? 6 : kRoom;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kHaloAStages * kHaloABytes + kBStages * kBStageBytes + kEpiBytes + 512 + 1024;
+  static constexpr int kSmemBytes = kAStages * kHaloABytes + kBStages * kBStageBytes + kEpiBytes + 512 + 1024;
   static_assert(kBStages >= 2, "weight ring needs at least two stages");
+  static_assert(BLOCK_N > 64 || kBStages >= 3, "resident 3x3 weights need three boxes");
 };
 
 template <int BLOCK_N, bool BF16>
@@ -570,7 +595,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
   using Cfg = HaloCfg<BLOCK_N>;
-  constexpr int SA = kHaloAStages, SB = Cfg::kBStages;
+  constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -930,10 +955,10 @@ static int effective_block_n(const ConvLayer& L, bool has_res) {
 // Output tensor map for the epilogue's TMA store: the 16-bit NHWC output viewed as [rows][Cout] (flat) or
 // [B][Ho][Wo][Cout] (spatial), one box = one column group (32 or 64 channels) of one tile's pixels.
 static int out_cols(int block_n) { return block_n >= 256 ? 64 : 32; }
-static int out_map_flat(CUtensorMap* map, ElemType elem, void* out, int ldc, int cout, long long rows, int block_n) {
+static int out_map_flat(CUtensorMap* map, ElemType elem, void* out, int ldc, int cout, long long rows, int block_n, int box_rows) {
   const uint64_t dims[2] = {(uint64_t)cout, (uint64_t)rows};
   const uint64_t strides[1] = {(uint64_t)ldc * 2};
-  const uint32_t box[2] = {(uint32_t)out_cols(block_n), (uint32_t)kBlockM};
+  const uint32_t box[2] = {(uint32_t)out_cols(block_n), (uint32_t)box_rows};
   const uint32_t es[2] = {1, 1};
   return encode_map(map, elem, 2, out, dims, strides, box, es, out_cols(block_n) == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
 }
@@ -944,6 +969,19 @@ static int out_map_spatial(CUtensorMap* map, ElemType elem, void* out, int ldc, 
   const uint32_t box[4] = {(uint32_t)out_cols(block_n), (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   const uint32_t es[4] = {1, 1, 1, 1};
   return encode_map(map, elem, 4, out, dims, strides, box, es, out_cols(block_n) == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+// MIMAMO_STORE_MODE = "<flat><strided 1x1><3x3>" digits (default "012") selects the epilogue store granularity per layer kind
+static int store_mode_setting(int kind) {
+  static int modes[3] = {-1, -1, -1};
+  if (modes[0] < 0) {
+    const char* e = getenv("MIMAMO_STORE_MODE");
+    const char* d = (e && strlen(e) == 3) ? e : "012";
+    for (int i = 0; i < 3; ++i) modes[i] = (d[i] >= '0' && d[i] <= '2') ? d[i] - '0' : i;
+    if (modes[1] == 0) modes[1] = 1;                          // per-warp boxes only exist for flat layers
+    if (modes[2] == 0) modes[2] = 1;
+  }
+  return modes[kind];
 }
 
 static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
@@ -1065,7 +1103,8 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
   CUtensorMap mo;
-  rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr));
+  p.store_mode = store_mode_setting(0);
+  rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr), p.store_mode == 0 ? 32 : kBlockM);
   if (rc) return rc;
   return launch(L, ma, mb, mo, p, stream);
 }
@@ -1117,6 +1156,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
         p.resident_w = (p.cin_blocks == 1 && p.n_tiles == 1 && !(e && e[0] == '0')) ? 1 : 0;
       }
       const bool bf = L.elem == kBF16;
+      p.store_mode = store_mode_setting(2);
       CUtensorMap mo;                                          // one box = bh padded lines; the two extra columns per line fall outside Wo and are clipped
       rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, line, bh, 1, bn_cols);
       if (rc) return rc;
@@ -1158,6 +1198,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
   CUtensorMap mo;
+  p.store_mode = store_mode_setting(L.ksize == 1 ? 1 : 2);
   rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, best_bw, best_bh, best_bn, effective_block_n(L, residual != nullptr));
   if (rc) return rc;
   return launch(L, ma, mb, mo, p, stream);
@@ -1194,6 +1235,7 @@ static int conv1_s2d_forward_windows(const ConvLayer& L, const void* s2d, int B,
   p.a_rows = bw * bh;
   p.m_tiles = p.tiles_w * p.tiles_h * B;
   CUtensorMap mo;
+  p.store_mode = 1;
   rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, bw, bh, 1, 64);
   if (rc) return rc;
   return launch(L, ma, mb, mo, p, stream);
@@ -1255,6 +1297,7 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * 64.0 * 256.0;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
+  p.store_mode = 1;
   CUtensorMap mo;                                              // one box = one 115-pixel padded line; columns >= 112 are clipped
   {
     int rc = out_map_spatial(&mo, L.elem, out, ldc, 64, Wo, Ho, B, S2D, 1, 1, 64);
@@ -1291,6 +1334,17 @@ extern "C" int mimamo_profile_gemm_read(double* total_ms, uint64_t* launches, do
   if (launches) *launches = g_prof_used;
   if (issued_flops) *issued_flops = g_prof_flops;
   return MIMAMO_OK;
+}
+
+// Per-launch durations (ms) of the launches recorded since mimamo_profile_gemm(1), in launch order; returns the count.
+extern "C" int mimamo_profile_gemm_launches(float* ms_out, int32_t max_launches) {
+  int n = 0;
+  for (size_t i = 0; i < g_prof_used && n < max_launches; ++i, ++n) {
+    float ms = 0.f;
+    MM_CUDA(cudaEventElapsedTime(&ms, g_prof_events[i].first, g_prof_events[i].second));
+    ms_out[n] = ms;
+  }
+  return n;
 }
 
 // Test hook (include/mimamo_b200.h): one convolution through the engine, bf16 NHWC in/out.
