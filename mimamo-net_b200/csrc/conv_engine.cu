@@ -47,9 +47,11 @@ struct ConvParams {
   const float* scale;
   const float* shift;
   const void* residual;
+  const void* a_ptr;         // conv1 line kernel: the space-to-depth'ed input (plain bulk copies, no tensor map)
   void* out;
   int ldc, ld_res;
   int relu;
+  int debug;                 // timing experiments only (MIMAMO_DEBUG): 1 = epilogue skips math+store, 2 = line kernel issues 4 of 16 UMMAs
   int store_mode;            // epilogue TMA store granularity: 0 = per warp (32 rows, flat layers), 1 = per column group, 2 = whole tile
   int resident_w;            // halo kernel: the whole 3x3 weight set stays in shared memory (Cin_p == 64, 9 taps <= kBStages boxes)
 };
@@ -233,7 +235,8 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
 template <int BLOCK_N, bool HAS_RES>
 struct GemmCfg {
   static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;                        // 16-bit [128][BLOCK_N] TMA-store staging
+  static constexpr int kEpiBufs = BLOCK_N <= 128 ? 2 : 1;                          // double-buffered staging where shared memory allows
+  static constexpr int kEpiBytes = kEpiBufs * kBlockM * BLOCK_N * 2;             // 16-bit [128][BLOCK_N] TMA-store staging
   static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
@@ -275,6 +278,7 @@ __device__ __forceinline__ void tma_store_4d(uint64_t map, uint32_t src, int c0,
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Epilogue warps (shared by all three kernels).  ncu on the first versions (profiles/gemm_r1_ncu_summary_v2.txt)
@@ -289,7 +293,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // written in the same swizzled row layout so that thread = row reads it back conflict-free.  (Pulling the residual
 // of later tiles into L2 first -- TMA prefetch or prefetch.global.L2 -- was measured 10-15 % SLOWER: these layers
 // are bound by bytes through L2, and a prefetch moves every residual byte through it twice.)
-template <int BLOCK_N, bool BF16, bool HAS_RES>
+template <int BLOCK_N, bool BF16, bool HAS_RES, int EPI_BUFS>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
                                                int num_tiles) {
@@ -302,8 +306,8 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
     constexpr int ROW_BYTES = COLS * 2;                       // staging row: 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B)
     if (half < PARTS) {
     const int row = quarter * 32 + lane;                      // accumulator row of this thread
-    const uint32_t stage_u32 = smem_u32(sEpi + half * (128 * ROW_BYTES));
-    const uint32_t my_row_u32 = stage_u32 + row * ROW_BYTES;
+    constexpr int BUF_BYTES = kBlockM * BLOCK_N * 2;         // one staging tile (all column groups)
+    const uint32_t stage0_u32 = smem_u32(sEpi + half * (128 * ROW_BYTES));
     const uint32_t swz = ROW_BYTES == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);   // XOR on the 16-byte chunk index
     const uint32_t res_u32 = smem_u32(sRes + ew * (kResDepth * 2048));
     const int sub_row = lane >> 2, pair = lane & 3;           // residual fetch: row (it*8 + sub_row), 16-byte piece `pair`
@@ -351,10 +355,14 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       const int n0 = n_tile * BLOCK_N + half * COLS;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      // the staging tile is free once the previous tile's TMA store has read it
-      if (issuer) tma_store_wait_read();
+      // staging tiles alternate (EPI_BUFS == 2): this one is free once the store issued two tiles ago has read it
+      const uint32_t buf_off = EPI_BUFS == 2 ? (uint32_t)(local & 1) * BUF_BYTES : 0u;
+      const uint32_t stage_u32 = stage0_u32 + buf_off;
+      const uint32_t my_row_u32 = stage_u32 + row * ROW_BYTES;
+      if (issuer) { if (EPI_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       sync_store_group();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
+      if (p.debug & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
         uint32_t v[32];
@@ -412,7 +420,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
         } else {
           const int g0 = store_mode == 1 ? half : 0, g1 = store_mode == 1 ? half + 1 : PARTS;
           for (int g = g0; g < g1; ++g) {
-            const uint32_t src = smem_u32(sEpi) + g * (128 * ROW_BYTES);
+            const uint32_t src = smem_u32(sEpi) + buf_off + g * (128 * ROW_BYTES);
             const int nc = n_tile * BLOCK_N + g * COLS;
             if (p.mode == 0) {
               tma_store_2d(map_out, src, nc, m_tile * kBlockM);
@@ -549,7 +557,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, HAS_RES>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -581,7 +589,8 @@ struct HaloCfg {
   // resident weights leave the room) keep three patches in flight.
   static constexpr int kAStages = BLOCK_N <= 64 ? 4 : 3;
   static constexpr int kBStageBytes = 3 * BLOCK_N * kBlockK * 2;          // the three taps of one kernel row
-  static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
+  static constexpr int kEpiBufs = 1;                                      // MMA-bound layers: the patch / weight rings need the room more
+  static constexpr int kEpiBytes = kEpiBufs * kBlockM * BLOCK_N * 2;
   static constexpr int kRoom = (232448 - 1024 - 512 - kEpiBytes - kAStages * kHaloABytes) / kBStageBytes;
   static constexpr int kBStages = kRoom > 6 ? 6 : kRoom;
   static constexpr int kTmemCols = 2 * BLOCK_N;
@@ -714,7 +723,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, false, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -726,30 +735,41 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // ---------------------------------------------------------------------------------------
 // conv1_7x7_s2 as a "line" kernel.  After space-to-depth the layer is a 4x4 / stride-1 convolution
-// over 16-channel pixels (32 bytes).  One tile = one output line (112 pixels): the 4 x 115-pixel input
-// patch is loaded once (14.7 KB, SWIZZLE_32B rows of one pixel each) and each of the 16 taps is a
-// K=16 UMMA on a row-shifted view of it; the whole 64 x 256 weight matrix (32 KB) stays resident.
-// Compared with materialising the 4 overlapping 128-byte windows per pixel through TMA (the
-// conv_gemm_kernel path, 96 KB of L2->SM fill per 128 pixels) the fill drops to 14.7 KB per line.
+// over 16-channel pixels.  One tile = one output line (112 pixels): the 4-row input patch is loaded once
+// and each of the 16 taps is a K=16 UMMA on a row-shifted view of it; the whole 64 x 256 weight matrix
+// (32 KB) stays resident.
+// The input is stored chunk-planar, [B][115 rows][2 chunks][115 px][8 ch] (nn_kernels.cuh): for a fixed
+// 16-byte channel chunk the pixels of a row are contiguous, which IS the un-swizzled K-major UMMA layout
+// (8-row core matrices of 128 contiguous bytes, SBO = 128 B; the second K chunk LBO = 1840 B further).
+// Four consecutive rows are one contiguous 14 720-byte block, fetched by a single cp.async.bulk.  The first
+// version of this kernel used a SWIZZLE_32B tensor map whose 460 32-byte box rows per tile kept the TMA unit
+// busy for ~1900 cycles (the kernel ran at 1.0 us per line against 0.27 us of MMA time).
 // ---------------------------------------------------------------------------------------
 constexpr int kLineABytes = 16384;
 constexpr int kLineAStages = 6;
 constexpr int kLineWBytes = 32768;
-constexpr uint32_t kDescHi32 = 16u | (1u << 14) | (6u << 29);   // SBO = 256 B, version 1, SWIZZLE_32B
-constexpr int kLineEpiBytes = kBlockM * 64 * 2;
+constexpr int kLinePlane = 115 * 16;                         // one (row, chunk) plane: 115 pixels x 16 B
+constexpr uint32_t kDescHi32 = 16u | (1u << 14) | (6u << 29);   // weights: SBO = 256 B, version 1, SWIZZLE_32B
+constexpr uint32_t kDescHiFlat = 8u | (1u << 14);               // patch: SBO = 128 B, version 1, no swizzle
+constexpr int kLineEpiBytes = 2 * kBlockM * 64 * 2;           // double-buffered staging
 constexpr int kLineSmemBytes = kLineWBytes + kLineAStages * kLineABytes + kLineEpiBytes + 512 + 1024;
 
+__device__ __forceinline__ void bulk_load_u32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void umma_one(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
-                                         uint32_t hi) {
+                                         uint32_t a_hi, uint32_t b_hi) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       ".reg .b64 da, db;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "mov.b64 da, {%1, %5};\n"
-      "mov.b64 db, {%2, %5};\n"
+      "mov.b64 db, {%2, %6};\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(a_hi), "r"(b_hi)
       : "memory");
 }
 
@@ -785,12 +805,13 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = p.m_tiles;                           // one N tile (Cout = 64)
-  const int lines = p.tiles_h, line = p.bw;                  // 112 output lines per image, 115-pixel padded line
+  const int lines = p.tiles_h;                               // 112 output lines per image
   if (warp == 0) {
     const bool leader = elect_one();
-    const uint32_t a_bytes = (uint32_t)p.a_rows * 32u;       // 4 * 115 pixels
+    const uint32_t a_bytes = 4u * 2u * kLinePlane;           // 4 rows x 2 chunks x 115 pixels x 16 B, contiguous in memory
     const uint32_t sA0 = smem_u32(sA), fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
-    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    const uint64_t mapB = reinterpret_cast<uint64_t>(&tmB);
+    const uint8_t* a_src = reinterpret_cast<const uint8_t*>(p.a_ptr);
     if (leader) {
       bar_expect_tx_u32(smem_u32(w_full), (uint32_t)kLineWBytes);
       tma3d_u32(smem_u32(sW), mapB, smem_u32(w_full), 0, 0, 0);
@@ -802,14 +823,15 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       bar_wait_u32(ea0 + sa * 8, pa);
       if (leader) {
         bar_expect_tx_u32(fa0 + sa * 8, a_bytes);
-        tma4d_u32(sA0 + sa * kLineABytes, mapA, fa0 + sa * 8, 0, 0, h, n_img);
+        bulk_load_u32(sA0 + sa * kLineABytes, a_src + ((size_t)n_img * 115 + h) * (2 * kLinePlane), a_bytes, fa0 + sa * 8);
       }
       if (++sa == SA) { sa = 0; pa ^= 1; }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
     const uint32_t idesc = p.idesc;
-    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), w_lo0 = desc_lo(smem_u32(sW));
+    const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFF) >> 4) | ((uint32_t)(kLinePlane >> 4) << 16);   // LBO = one chunk plane
+    const uint32_t w_lo0 = desc_lo(smem_u32(sW));
     const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
     const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
     bar_wait_u32(smem_u32(w_full), 0);
@@ -828,15 +850,15 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kh = 0; kh < 4; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 4; ++kw)
-            umma_one(d_tmem, a_base + (uint32_t)(kh * line + kw) * 2u, w_lo0 + (uint32_t)(kh * 4 + kw) * 128u, idesc,
-                     (kh | kw) != 0 ? 1u : 0u, kDescHi32);
+            if (!(p.debug & 2) || kh == 0) umma_one(d_tmem, a_base + (uint32_t)(kh * (2 * kLinePlane >> 4) + kw), w_lo0 + (uint32_t)(kh * 4 + kw) * 128u, idesc,
+                     (kh | kw) != 0 ? 1u : 0u, kDescHiFlat, kDescHi32);
         commit_u32(ea0 + sa * 8);
         commit_u32(tfull0 + acc * 8);
       }
       if (++sa == SA) { sa = 0; pa ^= 1; }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
   }
   tc_fence_before();
   __syncthreads();
@@ -1076,6 +1098,7 @@ static int fill_common(ConvParams& p, const ConvLayer& L, void* out, int ldc, co
   p.idesc = make_idesc(bn, L.elem);
   p.scale = L.scale_dev; p.shift = L.shift_dev;
   p.residual = residual; p.out = out; p.ldc = ldc; p.ld_res = ld_res; p.relu = L.relu;
+  { static int d = -1; if (d < 0) { const char* e = getenv("MIMAMO_DEBUG"); d = e ? atoi(e) : 0; } p.debug = d; }
   p.n_tiles = L.Cout / bn;
   p.cin_blocks = L.Cin_p / kBlockK;
   p.taps_w = L.ksize;
@@ -1204,67 +1227,21 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   return launch(L, ma, mb, mo, p, stream);
 }
 
-// conv1_7x7_s2 without an im2col buffer.  The input is space-to-depth'ed once (2x2 -> 12 (+4 zero)
-// channels, 115x115, padded by 4 original pixels so no coordinate is ever negative); the 7x7/s2
-// convolution becomes a 4x4/s1 one, and the 4 horizontally adjacent s2d pixels of a tap row are
-// 64 contiguous 16-bit values = exactly one 128-byte K block.  The activation tensor map therefore
-// addresses OVERLAPPING windows: dim1 = output column with a 32-byte global stride and a 128-byte
-// extent.  K = 4 rows x 64 = 256 (147 real taps, the rest zero weights).
-static int conv1_s2d_forward_windows(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
-  MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [Cout][256] layer");
-  if (B == 0) return MIMAMO_OK;
-  const int Wo = 112, Ho = 112, S2D = 115;
-  const int bw = 16, bh = 8;
-  CUtensorMap ma, mb;
-  const uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)S2D, (uint64_t)B};
-  const uint64_t strides[3] = {32, (uint64_t)S2D * 32, (uint64_t)S2D * S2D * 32};
-  const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
-  const uint32_t es[4] = {1, 1, 1, 1};
-  int rc = encode_map(&ma, L.elem, 4, s2d, dims, strides, box, es);
-  if (rc) return rc;
-  ConvParams p;
-  memset(&p, 0, sizeof(p));
-  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, nullptr, 0));
-  if (rc) return rc;
-  p.mode = 1;
-  p.cin_blocks = 1; p.taps_w = 1; p.num_k_blocks = 4;       // K block kb = tap row kb of the 4x4 s2d kernel
-  p.stride = 1; p.pad = 0;
-  p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
-  p.bw = bw; p.bh = bh; p.bn = 1;
-  p.tiles_w = Wo / bw; p.tiles_h = Ho / bh;
-  p.a_rows = bw * bh;
-  p.m_tiles = p.tiles_w * p.tiles_h * B;
-  CUtensorMap mo;
-  p.store_mode = 1;
-  rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, bw, bh, 1, 64);
-  if (rc) return rc;
-  return launch(L, ma, mb, mo, p, stream);
-}
-
-
-// conv1 over the space-to-depth'ed input: line kernel by default, overlapping-window GEMM with
-// MIMAMO_CONV1_LINE=0 (kept as the cross-check of the line kernel).
+// conv1 over the space-to-depth'ed, chunk-planar input (nn_kernels.cuh): the line kernel.
 int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
   MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1 && L.Cout == 64, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [64][256] layer");
-  const char* e = getenv("MIMAMO_CONV1_LINE");
-  if (e && e[0] == '0') return conv1_s2d_forward_windows(L, s2d, B, out, ldc, stream);
   if (B == 0) return MIMAMO_OK;
   const int S2D = 115, Wo = 112, Ho = 112;
   CUtensorMap ma, mb;
   {
-    const uint64_t dims[4] = {16, (uint64_t)S2D, (uint64_t)S2D, (uint64_t)B};
-    const uint64_t strides[3] = {32, (uint64_t)S2D * 32, (uint64_t)S2D * S2D * 32};
-    const uint32_t box[4] = {16, (uint32_t)S2D, 4, 1};
-    const uint32_t es[4] = {1, 1, 1, 1};
-    int rc = encode_map(&ma, L.elem, 4, s2d, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_32B);
-    if (rc) return rc;
     // weights [64][256] viewed as [tap (16)][n (64)][16 ch]: one box = the whole matrix, tap-major in smem
     const uint64_t wdims[3] = {16, 64, 16};
     const uint64_t wstr[2] = {512, 32};
     const uint32_t wbox[3] = {16, 64, 16};
     const uint32_t wes[3] = {1, 1, 1};
-    rc = encode_map(&mb, L.elem, 3, L.w_dev, wdims, wstr, wbox, wes, CU_TENSOR_MAP_SWIZZLE_32B);
+    int rc = encode_map(&mb, L.elem, 3, L.w_dev, wdims, wstr, wbox, wes, CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
+    ma = mb;                                                   // the patch needs no tensor map (plain bulk copies)
   }
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -1274,6 +1251,7 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
   p.bw = S2D; p.bh = 1; p.bn = 1;
   p.tiles_w = 1; p.tiles_h = Ho;
   p.a_rows = 4 * S2D;
+  p.a_ptr = s2d;
   p.m_tiles = Ho * B; p.n_tiles = 1;
   p.num_k_blocks = 4;                                        // K = 256 for the flop accounting
   static bool attr_set[2] = {false, false};

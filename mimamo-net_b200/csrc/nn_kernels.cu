@@ -116,8 +116,9 @@ __global__ void conv1_s2d_kernel(const float* __restrict__ x, long long B, uint4
     o0.z = v[4] | ((uint32_t)v[5] << 16); o0.w = v[6] | ((uint32_t)v[7] << 16);
     o1.x = v[8] | ((uint32_t)v[9] << 16); o1.y = v[10] | ((uint32_t)v[11] << 16);
     o1.z = 0; o1.w = 0;
-    out[i * 2] = o0;
-    out[i * 2 + 1] = o1;
+    const long long row = b * 115 + Y;                           // chunk-planar: [row][chunk][X]
+    out[(row * 2) * 115 + X] = o0;
+    out[(row * 2 + 1) * 115 + X] = o1;
   }
 }
 

@@ -13,8 +13,11 @@ int nchw_to_nhwc16(const float* src, int N, int C, int H, int W, void* dst, int 
                    ElemType elem, cudaStream_t s);
 // conv1_7x7_s2 lowering: fp32 NCHW [B][3][224][224] -> 16-bit [B*112*112][192] (K = c*49+kh*7+kw, zero padded)
 int im2col_conv1(const float* x, int B, void* a, ElemType elem, cudaStream_t s);
-// conv1 lowering without im2col: fp32 NCHW [B][3][224][224] -> 16-bit [B][115][115][16],
-// s2d[b][Y][X][(py*2+px)*3 + c] = x[b][c][2Y+py-4][2X+px-4] (zero outside / channels 12..15)
+// conv1 lowering without im2col: fp32 NCHW [B][3][224][224] -> 16-bit space-to-depth'ed, chunk-planar
+// [B][115 rows Y][2 chunks][115 px X][8 ch]:  value(b, Y, X, k = (py*2+px)*3 + c) = x[b][c][2Y+py-4][2X+px-4]
+// (zero outside the image and for k = 12..15), stored at chunk k / 8, lane k % 8.  For a fixed chunk the
+// pixels of a row are contiguous 16-byte units -- the un-swizzled K-major UMMA operand layout -- and four
+// consecutive rows form one contiguous block (conv_engine.cu, conv1_line_kernel).
 int conv1_space_to_depth(const float* x, int B, void* s2d, ElemType elem, cudaStream_t s);
 // pool1_3x3_s2: MaxPool(3, stride 2, pad 0, ceil_mode) on NHWC 16-bit
 int maxpool3x3s2_ceil(const void* x, int B, int H, int W, int C, void* out, ElemType elem, cudaStream_t s);

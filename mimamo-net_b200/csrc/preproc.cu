@@ -90,7 +90,7 @@ crops_gray_kernel(const __grid_constant__ PreprocDev P, const uint8_t* __restric
 
 // ---- RGB: one CTA per crop ----------------------------------------------------------------------
 // MODE 0: fp32 NCHW [n][3][crop][crop] (what the reference's Image_Sampler yields);
-// MODE 1 / 2: bf16 / fp16 space-to-depth'ed conv1 operand [n][115][115][16] (nn_kernels.cuh).
+// MODE 1 / 2: bf16 / fp16 space-to-depth'ed, chunk-planar conv1 operand [n][115][2][115][8] (nn_kernels.cuh).
 template <int MODE>
 __global__ void __launch_bounds__(kPreThreads)
 crops_rgb_kernel(const __grid_constant__ PreprocDev P, const uint8_t* __restrict__ crops, void* __restrict__ out_) {
@@ -166,8 +166,8 @@ crops_rgb_kernel(const __grid_constant__ PreprocDev P, const uint8_t* __restrict
       o0.z = h16[4] | ((uint32_t)h16[5] << 16); o0.w = h16[6] | ((uint32_t)h16[7] << 16);
       o1.x = h16[8] | ((uint32_t)h16[9] << 16); o1.y = h16[10] | ((uint32_t)h16[11] << 16);
       o1.z = 0; o1.w = 0;
-      out[i * 2] = o0;
-      out[i * 2 + 1] = o1;
+      out[((size_t)Y * 2) * D + X] = o0;                        // chunk-planar rows: [Y][chunk][X]
+      out[((size_t)Y * 2 + 1) * D + X] = o1;
     }
   }
 }
@@ -300,8 +300,8 @@ crops_rgb3_kernel(const __grid_constant__ PreprocDev P, const uint8_t* __restric
         o0.z = h16[a][4] | ((uint32_t)h16[a][5] << 16); o0.w = h16[a][6] | ((uint32_t)h16[a][7] << 16);
         o1.x = h16[a][8] | ((uint32_t)h16[a][9] << 16); o1.y = h16[a][10] | ((uint32_t)h16[a][11] << 16);
         o1.z = 0; o1.w = 0;
-        out[((size_t)Y * D + X) * 2] = o0;
-        out[((size_t)Y * D + X) * 2 + 1] = o1;
+        out[((size_t)Y * 2) * D + X] = o0;                      // chunk-planar rows: [Y][chunk][X]
+        out[((size_t)Y * 2 + 1) * D + X] = o1;
       }
     }
   }
