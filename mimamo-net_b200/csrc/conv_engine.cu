@@ -773,7 +773,26 @@ __device__ __forceinline__ void umma_one(uint32_t d_tmem, uint32_t a_lo, uint32_
       : "memory");
 }
 
+// POOL = true additionally fuses pool1_3x3_s2 (MaxPool 3x3, stride 2, pad 0, ceil_mode; 112x112 -> 56x56) into the
+// epilogue, so the 1.6 MB-per-image conv1 output is never written or re-read.  A CTA then walks bands of 8 pooled
+// rows (conv rows 16b .. 16b+16): the vertical maximum over three conv rows is an elementwise max of three
+// consecutive tiles in the SAME thread (thread = output column, 32 channels; the shared row 2i+2 is carried over in
+// registers), and the horizontal 3-wide / stride-2 maximum goes through a double-buffered shared-memory line.  The
+// maximum is taken on the 16-bit rounded post-BN/ReLU values, i.e. exactly what a separate pooling kernel would read.
+constexpr int kPoolBand = 8;                                 // pooled rows per work unit
+constexpr int kPoolBands = 56 / kPoolBand;
+
 template <bool BF16>
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  if (BF16) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <bool BF16, bool POOL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
@@ -791,9 +810,8 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmOut);
+    if (!POOL) tma_prefetch_desc(&tmOut);
     for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * 2); }
@@ -804,8 +822,20 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = p.m_tiles;                           // one N tile (Cout = 64)
   const int lines = p.tiles_h;                               // 112 output lines per image
+  // Work list of this CTA.  !POOL: tiles (image, line) round-robin.  POOL: units (image, band) round-robin, each
+  // expanding to its 17 (last band: 16) consecutive conv lines.  Every role walks the same list.
+  const int num_units = POOL ? p.Nimg * kPoolBands : p.m_tiles;
+  auto first_line = [&](int unit, int& n_img, int& h0, int& count) {
+    if (POOL) {
+      n_img = unit / kPoolBands;
+      const int band = unit - n_img * kPoolBands;
+      h0 = band * 2 * kPoolBand;
+      count = band == kPoolBands - 1 ? 2 * kPoolBand : 2 * kPoolBand + 1;      // conv row 112 does not exist (ceil_mode clips)
+    } else {
+      n_img = unit / lines; h0 = unit - n_img * lines; count = 1;
+    }
+  };
   if (warp == 0) {
     const bool leader = elect_one();
     const uint32_t a_bytes = 4u * 2u * kLinePlane;           // 4 rows x 2 chunks x 115 pixels x 16 B, contiguous in memory
@@ -818,14 +848,18 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     int sa = 0; uint32_t pa = 1;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_img = tile / lines, h = tile - n_img * lines;
-      bar_wait_u32(ea0 + sa * 8, pa);
-      if (leader) {
-        bar_expect_tx_u32(fa0 + sa * 8, a_bytes);
-        bulk_load_u32(sA0 + sa * kLineABytes, a_src + ((size_t)n_img * 115 + h) * (2 * kLinePlane), a_bytes, fa0 + sa * 8);
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int n_img, h0, count;
+      first_line(unit, n_img, h0, count);
+#pragma unroll 1
+      for (int h = h0; h < h0 + count; ++h) {
+        bar_wait_u32(ea0 + sa * 8, pa);
+        if (leader) {
+          bar_expect_tx_u32(fa0 + sa * 8, a_bytes);
+          bulk_load_u32(sA0 + sa * kLineABytes, a_src + ((size_t)n_img * 115 + h) * (2 * kLinePlane), a_bytes, fa0 + sa * 8);
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
-      if (++sa == SA) { sa = 0; pa ^= 1; }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
@@ -838,27 +872,118 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int sa = 0; uint32_t pa = 0;
     int local = 0;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const uint32_t acc = local & 1;
-      bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
-      bar_wait_u32(fa0 + sa * 8, pa);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        const uint32_t a_base = a_lo0 + sa * (kLineABytes >> 4);
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int n_img, h0, count;
+      first_line(unit, n_img, h0, count);
+#pragma unroll 1
+      for (int h = h0; h < h0 + count; ++h, ++local) {
+        const uint32_t acc = local & 1;
+        bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
+        bar_wait_u32(fa0 + sa * 8, pa);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          const uint32_t a_base = a_lo0 + sa * (kLineABytes >> 4);
 #pragma unroll
-        for (int kh = 0; kh < 4; ++kh)
+          for (int kh = 0; kh < 4; ++kh)
 #pragma unroll
-          for (int kw = 0; kw < 4; ++kw)
-            if (!(p.debug & 2) || kh == 0) umma_one(d_tmem, a_base + (uint32_t)(kh * (2 * kLinePlane >> 4) + kw), w_lo0 + (uint32_t)(kh * 4 + kw) * 128u, idesc,
-                     (kh | kw) != 0 ? 1u : 0u, kDescHiFlat, kDescHi32);
-        commit_u32(ea0 + sa * 8);
-        commit_u32(tfull0 + acc * 8);
+            for (int kw = 0; kw < 4; ++kw)
+              if (!(p.debug & 2) || kh == 0) umma_one(d_tmem, a_base + (uint32_t)(kh * (2 * kLinePlane >> 4) + kw), w_lo0 + (uint32_t)(kh * 4 + kw) * 128u, idesc,
+                       (kh | kw) != 0 ? 1u : 0u, kDescHiFlat, kDescHi32);
+          commit_u32(ea0 + sa * 8);
+          commit_u32(tfull0 + acc * 8);
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
       }
-      if (++sa == SA) { sa = 0; pa ^= 1; }
     }
-  } else {
-    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+  } else if (!POOL) {
+    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles);
+  } else if (((warp - 2) >> 2) < 2) {
+    // ---- fused BN + ReLU + max pool epilogue: 8 warps, thread = output column dw, 32 channels ----
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int dw = quarter * 32 + lane;
+    const int et = half * 128 + dw;                          // 0..255: index among the epilogue threads
+    const uint32_t stage0 = smem_u32(sEpi);                  // two lines of [128 columns][64 ch] 16-bit, 128 B rows, XOR-swizzled 16 B chunks
+    const float4* sc = reinterpret_cast<const float4*>(p.scale + half * 32);
+    const float4* sh = reinterpret_cast<const float4*>(p.shift + half * 32);
+    uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
+    int local = 0, emits = 0;
+#pragma unroll 1
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int n_img, h0, count;
+      first_line(unit, n_img, h0, count);
+      uint32_t carry[16], m[16];
+#pragma unroll 1
+      for (int pos = 0; pos < count; ++pos, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 32;
+        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        uint32_t w[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 s4 = __ldg(sc + g), t4 = __ldg(sh + g);
+          const float o0 = fmaxf(__uint_as_float(v[4 * g]) * s4.x + t4.x, 0.f), o1 = fmaxf(__uint_as_float(v[4 * g + 1]) * s4.y + t4.y, 0.f);
+          const float o2 = fmaxf(__uint_as_float(v[4 * g + 2]) * s4.z + t4.z, 0.f), o3 = fmaxf(__uint_as_float(v[4 * g + 3]) * s4.w + t4.w, 0.f);
+          w[2 * g] = pack2<BF16>(o0, o1);
+          w[2 * g + 1] = pack2<BF16>(o2, o3);
+        }
+        const bool last = pos == count - 1;
+        bool emit = false;
+        if (pos == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) carry[j] = w[j];
+        } else if (pos & 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m[j] = hmax2_u32<BF16>(carry[j], w[j]);
+          emit = last;                                         // rows 110, 111 only: the bottom pooled row of the image
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { m[j] = hmax2_u32<BF16>(m[j], w[j]); carry[j] = w[j]; }
+          emit = true;
+        }
+        if (emit) {                                            // warp-uniform: pos and count are
+          const int prow = (h0 >> 1) + ((pos - 1) >> 1);       // pooled row
+          const uint32_t buf = stage0 + (uint32_t)(emits & 1) * (128 * 128);
+          ++emits;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t chunk = (uint32_t)(half * 4 + g);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + dw * 128 + ((chunk ^ (uint32_t)(dw & 7)) << 4)),
+                         "r"(m[4 * g]), "r"(m[4 * g + 1]), "r"(m[4 * g + 2]), "r"(m[4 * g + 3]) : "memory");
+          }
+          named_bar_sync(1, 256);
+          // horizontal 3-wide / stride-2 maximum: item = (pooled column j, 16-byte channel chunk c)
+          for (int it = et; it < 56 * 8; it += 256) {
+            const int j = it >> 3, c = it & 7;
+            uint32_t r0[4], r1[4];
+            {
+              const int x = 2 * j;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3])
+                           : "r"(buf + x * 128 + (((uint32_t)c ^ (uint32_t)(x & 7)) << 4)));
+            }
+#pragma unroll
+            for (int d = 1; d < 3; ++d) {
+              const int x = 2 * j + d;
+              if (x < 112) {
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3])
+                             : "r"(buf + x * 128 + (((uint32_t)c ^ (uint32_t)(x & 7)) << 4)));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r0[q] = hmax2_u32<BF16>(r0[q], r1[q]);
+              }
+            }
+            *reinterpret_cast<uint4*>(out + ((((size_t)n_img * 56 + prow) * 56 + j) * 64 + c * 8)) = make_uint4(r0[0], r0[1], r0[2], r0[3]);
+          }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1228,8 +1353,9 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
 }
 
 // conv1 over the space-to-depth'ed, chunk-planar input (nn_kernels.cuh): the line kernel.
-int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream) {
+int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream, bool pool) {
   MM_REQUIRE(L.Cin_p == 256 && L.ksize == 1 && L.Cout == 64, MIMAMO_E_VALUE, "conv1_s2d_forward needs the packed [64][256] layer");
+  MM_REQUIRE(!pool || ldc == 64, MIMAMO_E_VALUE, "the fused pool1 output is a dense [B][56][56][64] tensor");
   if (B == 0) return MIMAMO_OK;
   const int S2D = 115, Wo = 112, Ho = 112;
   CUtensorMap ma, mb;
@@ -1254,14 +1380,17 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
   p.a_ptr = s2d;
   p.m_tiles = Ho * B; p.n_tiles = 1;
   p.num_k_blocks = 4;                                        // K = 256 for the flop accounting
-  static bool attr_set[2] = {false, false};
+  static bool attr_set = false;
   const bool bf = L.elem == kBF16;
-  if (!attr_set[bf]) {
-    if (bf) MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
-    else MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
-    attr_set[bf] = true;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
+    attr_set = true;
   }
-  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  const int units = pool ? B * kPoolBands : p.m_tiles;
+  const int grid = units < num_sms() ? units : num_sms();
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profile) {
     if (g_prof_used == g_prof_events.size()) {
@@ -1281,8 +1410,13 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
     int rc = out_map_spatial(&mo, L.elem, out, ldc, 64, Wo, Ho, B, S2D, 1, 1, 64);
     if (rc) return rc;
   }
-  if (bf) conv1_line_kernel<true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
-  else conv1_line_kernel<false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+  if (pool) {
+    if (bf) conv1_line_kernel<true, true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+    else conv1_line_kernel<false, true><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+  } else {
+    if (bf) conv1_line_kernel<true, false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+    else conv1_line_kernel<false, false><<<grid, kGemmThreads, kLineSmemBytes, stream>>>(ma, mb, mo, p);
+  }
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;

@@ -46,6 +46,7 @@ int out_size(int in, int k, int s, int p);
 
 // conv1_7x7_s2 over a space-to-depth'ed input (see nn_kernels: conv1_space_to_depth); L holds the
 // re-packed [64][256] weights.
-int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream);
+// pool = true fuses pool1_3x3_s2 (ceil_mode) into the epilogue: out is then the pooled [B][56][56][64] tensor
+int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int ldc, cudaStream_t stream, bool pool = false);
 
 }  // namespace mimamo

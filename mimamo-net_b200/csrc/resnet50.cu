@@ -32,6 +32,7 @@ struct mimamo_resnet50 {
   ConvLayer conv1;                 // 7x7 s2 as a 4x4 s1 conv over the space-to-depth'ed input (K = 256)
   ConvLayer conv1_im2col;          // fallback lowering: K = 147 -> 192 GEMM over an im2col buffer
   bool use_im2col = false;         // MIMAMO_CONV1=im2col
+  bool fuse_pool = true;           // MIMAMO_CONV1_POOL=0: separate pool1 kernel (cross-check of the fused epilogue)
   std::vector<ResBlock> blocks;
   int chunk = 512;                 // images per pass: larger chunks amortise per-launch ramp/tail (measured 128: 41.4 ms, 512: 37.6 ms per 2048 images)
 };
@@ -70,6 +71,8 @@ extern "C" int mimamo_resnet50_create(const mimamo_tensor_desc* tensors, int32_t
   if (ck && atoi(ck) > 0) net->chunk = atoi(ck);
   const char* c1 = getenv("MIMAMO_CONV1");
   net->use_im2col = c1 && strcmp(c1, "im2col") == 0;
+  const char* fp = getenv("MIMAMO_CONV1_POOL");
+  net->fuse_pool = !(fp && fp[0] == '0');
   int rc = make_conv(T, "conv1_7x7_s2", 64, 3, 7, 2, 3, 1, net->elem, net->conv1_im2col, 147);
   if (!rc) {
     // re-pack [64][3][7][7] into the s2d kernel [64][kh'(4)][kw'(4)][(py*2+px)*3+c (16)]
@@ -142,18 +145,21 @@ static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mi
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = batch - b0 < chunk ? batch - b0 : chunk;
     int rc;
+    bool pooled = false;                                       // conv1 kernel already produced pool1's output in X
     if (crops) {
       // resize + centre crop + mean subtraction straight into the space-to-depth'ed conv1 operand
       rc = crops_rgb_launch(pre, crops + (size_t)b0 * crop_edge * crop_edge * 3, Bc, A0, net->elem == kBF16 ? 1 : 2, stream);
-      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, C1, 64, stream);
+      pooled = net->fuse_pool;
+      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, pooled ? X : C1, 64, stream, pooled);
     } else if (net->use_im2col) {
       rc = im2col_conv1(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
       if (!rc) rc = gemm_forward(net->conv1_im2col, A0, Bc * 12544, C1, 64, nullptr, 0, stream);
     } else {
       rc = conv1_space_to_depth(x + (size_t)b0 * 3 * 224 * 224, Bc, A0, net->elem, stream);
-      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, C1, 64, stream);
+      pooled = net->fuse_pool;
+      if (!rc) rc = conv1_s2d_forward(net->conv1, A0, Bc, pooled ? X : C1, 64, stream, pooled);
     }
-    if (!rc) rc = maxpool3x3s2_ceil(C1, Bc, 112, 112, 64, X, net->elem, stream);
+    if (!rc && !pooled) rc = maxpool3x3s2_ceil(C1, Bc, 112, 112, 64, X, net->elem, stream);
     uint16_t* cur = X;
     uint16_t* nxt = Y;
     int H = 56;

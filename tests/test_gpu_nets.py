@@ -16,7 +16,8 @@ def _rgb(n, seed):
     return torch.randint(0, 256, (n, 3, 224, 224), generator=g).float() - torch.tensor(O.RESNET_MEAN)[None, :, None, None]
 
 
-@pytest.mark.parametrize("dtype,rel_tol,conv1", [("bf16", 4e-2, "line"), ("fp16", 6e-3, "line"), ("bf16", 4e-2, "im2col")])
+@pytest.mark.parametrize("dtype,rel_tol,conv1", [("bf16", 4e-2, "line"), ("fp16", 6e-3, "line"), ("bf16", 4e-2, "im2col"),
+                                                 ("bf16", 4e-2, "line_unfused_pool")])
 def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     """Row R: parity against the restated architecture with seeded synthetic weights (parity with
     the published checkpoint is unpinned: the third-party definition/weights are absent).
@@ -25,6 +26,7 @@ def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     monkeypatch.setenv("MIMAMO_RESNET_DTYPE", dtype)
     # conv1 lowerings: line kernel over the space-to-depth'ed input (default), explicit im2col GEMM (cross-check)
     monkeypatch.setenv("MIMAMO_CONV1", "im2col" if conv1 == "im2col" else "s2d")
+    monkeypatch.setenv("MIMAMO_CONV1_POOL", "0" if conv1 == "line_unfused_pool" else "1")    # pool1 fused into conv1's epilogue (default) or separate
     net = O.resnet_synthetic(1)
     x = _rgb(5, 21)
     ref = O.resnet_pool5(net, x)
@@ -40,6 +42,18 @@ def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     # batch composition must not matter (chunking / tile boundaries)
     again = ext.features(x[1:4].to(cuda)).cpu()
     assert torch.equal(again, got[1:4])
+
+
+def test_fused_pool1_is_bit_identical(cuda, monkeypatch):
+    """pool1 fused into conv1's epilogue takes the maximum of the same 16-bit values a separate pooling kernel reads."""
+    from resnet50_extractor import Resnet50_Extractor
+    net = O.resnet_synthetic(1)
+    x = _rgb(3, 33).to(cuda)
+    monkeypatch.setenv("MIMAMO_CONV1_POOL", "1")
+    fused = Resnet50_Extractor(model=net).features(x)
+    monkeypatch.setenv("MIMAMO_CONV1_POOL", "0")
+    unfused = Resnet50_Extractor(model=net).features(x)
+    assert torch.equal(fused, unfused)
 
 
 @pytest.mark.parametrize("name", ["head_b3", "head_b1"])
