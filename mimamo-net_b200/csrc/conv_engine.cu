@@ -814,7 +814,7 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (!POOL) tma_prefetch_desc(&tmOut);
     for (int i = 0; i < SA; ++i) { mbar_init(&full_a[i], 1); mbar_init(&empty_a[i], 1); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], POOL ? 16 : 8); }   // arrivals = active epilogue warps
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
@@ -898,37 +898,37 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (!POOL) {
     epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles);
-  } else if (((warp - 2) >> 2) < 2) {
-    // ---- fused BN + ReLU + max pool epilogue: 8 warps, thread = output column dw, 32 channels ----
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+  } else {
+    // ---- fused BN + ReLU + max pool epilogue: all 16 warps, thread = output column dw, 16 channels.  (With 8 warps
+    // of 32 channels the epilogue ran at 0.86 us per line against 0.64 us of load + MMA: two warps per scheduler
+    // cannot hide the latencies of this ~250-instruction dependent chain; ncu source view, profiles/.) ----
+    const int ew = warp - 2, quarter = warp & 3, part = ew >> 2;        // part: channels [16*part, 16*part + 16)
     const int dw = quarter * 32 + lane;
-    const int et = half * 128 + dw;                          // 0..255: index among the epilogue threads
+    const int et = part * 128 + dw;                          // 0..511: index among the epilogue threads
     const uint32_t stage0 = smem_u32(sEpi);                  // two lines of [128 columns][64 ch] 16-bit, 128 B rows, XOR-swizzled 16 B chunks
-    const float4* sc = reinterpret_cast<const float4*>(p.scale + half * 32);
-    const float4* sh = reinterpret_cast<const float4*>(p.shift + half * 32);
+    const float4* sc = reinterpret_cast<const float4*>(p.scale + part * 16);
+    const float4* sh = reinterpret_cast<const float4*>(p.shift + part * 16);
     uint16_t* out = reinterpret_cast<uint16_t*>(p.out);
     int local = 0, emits = 0;
 #pragma unroll 1
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       int n_img, h0, count;
       first_line(unit, n_img, h0, count);
-      uint32_t carry[16], m[16];
+      uint32_t carry[8], m[8];
 #pragma unroll 1
       for (int pos = 0; pos < count; ++pos, ++local) {
         const int acc = local & 1;
         mbar_wait(&tmem_full[acc], (local >> 1) & 1);
         tc_fence_after();
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * 32;
-        tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + part * 16, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        uint32_t w[16];
+        uint32_t w[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           const float4 s4 = __ldg(sc + g), t4 = __ldg(sh + g);
           const float o0 = fmaxf(__uint_as_float(v[4 * g]) * s4.x + t4.x, 0.f), o1 = fmaxf(__uint_as_float(v[4 * g + 1]) * s4.y + t4.y, 0.f);
           const float o2 = fmaxf(__uint_as_float(v[4 * g + 2]) * s4.z + t4.z, 0.f), o3 = fmaxf(__uint_as_float(v[4 * g + 3]) * s4.w + t4.w, 0.f);
@@ -939,30 +939,30 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         bool emit = false;
         if (pos == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) carry[j] = w[j];
+          for (int j = 0; j < 8; ++j) carry[j] = w[j];
         } else if (pos & 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[j] = hmax2_u32<BF16>(carry[j], w[j]);
+          for (int j = 0; j < 8; ++j) m[j] = hmax2_u32<BF16>(carry[j], w[j]);
           emit = last;                                         // rows 110, 111 only: the bottom pooled row of the image
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { m[j] = hmax2_u32<BF16>(m[j], w[j]); carry[j] = w[j]; }
+          for (int j = 0; j < 8; ++j) { m[j] = hmax2_u32<BF16>(m[j], w[j]); carry[j] = w[j]; }
           emit = true;
         }
-        if (emit) {                                            // warp-uniform: pos and count are
+        if (emit) {                                            // CTA-uniform: pos and count are
           const int prow = (h0 >> 1) + ((pos - 1) >> 1);       // pooled row
           const uint32_t buf = stage0 + (uint32_t)(emits & 1) * (128 * 128);
           ++emits;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t chunk = (uint32_t)(half * 4 + g);
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t chunk = (uint32_t)(part * 2 + g);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf + dw * 128 + ((chunk ^ (uint32_t)(dw & 7)) << 4)),
                          "r"(m[4 * g]), "r"(m[4 * g + 1]), "r"(m[4 * g + 2]), "r"(m[4 * g + 3]) : "memory");
           }
-          named_bar_sync(1, 256);
+          named_bar_sync(1, 512);
           // horizontal 3-wide / stride-2 maximum: item = (pooled column j, 16-byte channel chunk c)
-          for (int it = et; it < 56 * 8; it += 256) {
-            const int j = it >> 3, c = it & 7;
+          if (et < 56 * 8) {
+            const int j = et >> 3, c = et & 7;
             uint32_t r0[4], r1[4];
             {
               const int x = 2 * j;

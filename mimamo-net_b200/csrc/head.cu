@@ -10,6 +10,7 @@
 #include "conv_engine.cuh"
 #include "nn_kernels.cuh"
 #include "tensor_table.cuh"
+#include <stdlib.h>
 
 using namespace mimamo;
 
@@ -64,6 +65,7 @@ extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_t
   TensorTable T{tensors, n_tensors};
   mimamo_head* h = new mimamo_head();
   h->num_phase = num_phase; h->cin0 = 2 * num_phase;
+  { const char* e = getenv("MIMAMO_HEAD_CHUNK"); if (e && atoi(e) > 0) h->conv_chunk = atoi(e); }
   const int c0 = h->cin0;
   int rc = make_linear(T, "mlp.mlp.1", "mlp.mlp.2", 256, 2048, 1, true, h->mlp1);
   if (!rc) rc = make_linear(T, "mlp.mlp.5", "mlp.mlp.6", 256, 256, 1, true, h->mlp2);

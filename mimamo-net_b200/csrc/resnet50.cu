@@ -34,7 +34,8 @@ struct mimamo_resnet50 {
   bool use_im2col = false;         // MIMAMO_CONV1=im2col
   bool fuse_pool = true;           // MIMAMO_CONV1_POOL=0: separate pool1 kernel (cross-check of the fused epilogue)
   std::vector<ResBlock> blocks;
-  int chunk = 512;                 // images per pass: larger chunks amortise per-launch ramp/tail (measured 128: 41.4 ms, 512: 37.6 ms per 2048 images)
+  int chunk = 2048;                // images per pass: larger chunks amortise per-launch ramp/tail (measured per 2048 images: 128: 41.4 ms, 512: 37.6 ms
+                                   // on the first engine; 512: 28.3, 1024: 27.2, 2048: 26.5 ms now); 12 MB of workspace per image
 };
 
 static const size_t kPerImageElems =
