@@ -105,17 +105,24 @@ class Phase_Difference_Extractor(object):
                                            _native.dptr(ws), ws.numel(), _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
-    def phase_difference_indexed(self, frames, window_index):
+    def phase_difference_indexed(self, frames, window_index, out=None):
         """Clip variant of phase_difference: frames (n, W, H) are transformed
         once each; window_index (n_windows, T) int32 names the frames of every window (the clamp rule
         of api/sampler/snippet_sampler.py:144-152).  Returns per level (n_windows, nbands, T-1, c, c),
-        bit-identical to phase_difference(frames[window_index])."""
+        bit-identical to phase_difference(frames[window_index]).  `out`: optional list of preallocated contiguous
+        float32 tensors (one per level, n_windows*nbands*(T-1)*c*c elements each) to write into."""
         n, W, H = frames.size()
         n_windows, T = window_index.size()
         assert window_index.dtype == torch.int32 and window_index.device == frames.device
         plan, _, _, frames = self._prepare(frames.view(n, 1, W, H), True)
-        outs = [torch.empty((n_windows, self.nbands, T - 1, c, c), dtype=torch.float32, device=frames.device)
-                for c in plan.crops]
+        if out is None:
+            outs = [torch.empty((n_windows, self.nbands, T - 1, c, c), dtype=torch.float32, device=frames.device)
+                    for c in plan.crops]
+        else:
+            outs = list(out)
+            for o, c in zip(outs, plan.crops):
+                assert o.is_contiguous() and o.dtype == torch.float32 and o.device == frames.device \
+                    and o.numel() == n_windows * self.nbands * (T - 1) * c * c, 'bad preallocated output'
         if n_windows == 0 or T < 2:
             return outs[0] if isinstance(self.extract_level, int) else outs
         window_index = window_index.contiguous()

@@ -214,11 +214,48 @@ class Tester(object):
             feats = self.resnet50_extractor.features_from_crops(flat, pre).view(b, f, 2048)
             return self.model([phase_0, phase_1], feats)
 
-    def infer_crops_host(self, crops, to_host=True):
+    def infer_crops_host(self, crops, to_host=True, parts=4):
         """infer_crops from a HOST uint8 tensor (pinned for an asynchronous copy): 37.6 KB per frame cross
-        PCIe instead of the 722 KB of fp32 windows + RGB the reference's DataLoader ships."""
+        PCIe instead of the 722 KB of fp32 windows + RGB the reference's DataLoader ships.  The clips are
+        copied in `parts` groups on a copy stream; the gray / pyramid / phase stage of a group (clips are
+        independent there) starts as soon as its crops have landed, so only the first group's copy is exposed.
+        ResNet50 and the head then run once over the whole batch (bit-identical to infer_crops)."""
         device = get_device()
-        out = self.infer_crops(crops.to(device, non_blocking=True))
+        b, f = crops.shape[0], crops.shape[1]
+        main = torch.cuda.current_stream(device)
+        if getattr(self, '_crop_copy_stream', None) is None:
+            self._crop_copy_stream = torch.cuda.Stream(device)
+        copy = self._crop_copy_stream
+        parts = max(1, min(parts, b))
+        bounds = [(b * k) // parts for k in range(parts + 1)]
+        with torch.no_grad():
+            dev = torch.empty(crops.shape, dtype=torch.uint8, device=device)
+            copy.wait_stream(main)
+            landed = []
+            with torch.cuda.stream(copy):
+                for k in range(parts):
+                    dev[bounds[k]:bounds[k + 1]].copy_(crops[bounds[k]:bounds[k + 1]], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                    landed.append(ev)
+            dev.record_stream(copy)
+            pre = self.crop_preprocessor()
+            phase = None
+            for k in range(parts):
+                lo, hi = bounds[k], bounds[k + 1]
+                if hi == lo:
+                    continue
+                main.wait_event(landed[k])
+                flat = dev[lo:hi].reshape((hi - lo) * f, dev.shape[2], dev.shape[3], dev.shape[4])
+                idx = self.clip_window_index(hi - lo, f, device)
+                if phase is None:
+                    nb, T = self.phase_difference_extractor.nbands, self.num_phase + 1
+                    sizes = [self.phase_size, self.phase_size // 2]
+                    phase = [torch.empty((b, f, nb * (T - 1), c, c), dtype=torch.float32, device=device) for c in sizes]
+                self.phase_difference_extractor.phase_difference_indexed(pre.gray(flat), idx, out=[p[lo:hi] for p in phase])
+            flat = dev.reshape(b * f, dev.shape[2], dev.shape[3], dev.shape[4])
+            feats = self.resnet50_extractor.features_from_crops(flat, pre).view(b, f, 2048)
+            out = self.model([phase[0], phase[1]], feats)
         return out.cpu() if to_host else out
 
 
