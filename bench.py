@@ -29,6 +29,11 @@ CLIPS, FRAMES, T, SIZE = 32, 64, 13, 48
 WINDOWS = CLIPS * FRAMES
 RESNET_FLOP = 7.712e9            # per image (3856 MMAC)
 PHASENET_FLOP = 0.393e9          # per window
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 kernels from one `ncu --set full` capture of a
+# 512-image ResNet50 pass (profiles/gemm_r1_ncu_final.txt): 22.28 GB over its 53 launches, 0.92x the algorithmic 24.16 GB.
+# Traffic scales with the images per pass; the 12 PhaseNet launches per step were not captured (they move < 3 % of the bytes).
+NCU_DRAM_BYTES_PER_IMAGE = 22.28e9 / 512
+ALGO_BYTES_PER_IMAGE = 24.16e9 / 512
 METRIC = "face-windows/sec end-to-end V/A inference"
 UNIT = "windows/s"
 
@@ -274,9 +279,13 @@ def main():
                 "h2d_bytes_per_step": world * crops_h.numel(),
                 "d2h_bytes_per_step": world * (world if world > 1 else 1) * CLIPS * FRAMES * 2 * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: ResNet50 + PhaseNet convs)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 convolution engine: conv_gemm_kernel / conv3x3_halo_kernel / conv1_line_kernel (ResNet50 + PhaseNet convs)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                     "frac": (achieved_tf / peak_tf) if achieved_tf else None,
+                     "traffic": NCU_DRAM_BYTES_PER_IMAGE * WINDOWS * args.steps / gemm_n.value if gemm_n.value else None,
+                     "traffic_unit": "bytes per launch (ncu dram read+write of a 512-image pass, scaled to this run's images per launch)",
+                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_IMAGE * WINDOWS * args.steps / gemm_n.value if gemm_n.value else None,
+                     "algorithmic_flop_per_launch": algo_flops / gemm_n.value if gemm_n.value else None,
                      "peak_source": peak_src, "kernel_ms_per_step": gemm_ms.value / args.steps,
                      "kernel_share_of_step": gemm_ms.value / ms if ms else None,
                      "launches_per_step": gemm_n.value / args.steps,

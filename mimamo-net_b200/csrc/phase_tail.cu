@@ -52,7 +52,7 @@ __device__ __forceinline__ float unwrap_correction(float dd) {
 
 __global__ void __launch_bounds__(kTailThreads)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
-                  const TailGeom g, const int* __restrict__ root, int nb, int coeff_T) {
+                  const TailGeom g, const int* __restrict__ root, int nb, int coeff_T, int polar) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp;
   const int n_in = rin * cin, n_out = trp * tcp;
@@ -117,8 +117,10 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       for (int u = 0; u < 4; ++u) {
         const int c = cell[u];
         if (c < 0) continue;
-        const float ph = atan2f(v[u].y, v[u].x);
-        const float mag = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].x, v[u].x))), 1e-10f);
+        // polar: the fused paths converted each distinct frame to (phase, magnitude) once (coeff_to_polar_kernel),
+        // so the 13 windows sharing a frame do not repeat the atan2 / sqrt
+        const float ph = polar ? v[u].x : atan2f(v[u].y, v[u].x);
+        const float mag = polar ? v[u].y : __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].x, v[u].x))), 1e-10f);
         float up = ph;
         if (t > 0) {
           cum[c] += (double)unwrap_correction(__fsub_rn(ph, prev[c]));   // torch CPU cumsum: double acc
@@ -257,7 +259,7 @@ static int tail_setup() {
 
 int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, float* out,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const int* root = nullptr,
-                         int nb = 1, int coeff_T = 0) {
+                         int nb = 1, int coeff_T = 0, int polar = 0) {
   MM_REQUIRE(coeff && out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "phase_extract needs T >= 2 frames and a non-empty map");
   if (n_maps == 0) return MIMAMO_OK;
@@ -271,7 +273,7 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
   const int threads = g.tile_r * g.tile_c >= 1600 ? kTailThreads : (g.tile_r * g.tile_c >= 400 ? 256 : 128);   // small maps: fewer idle threads per barrier
-  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T);
+  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T, polar);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
     const long long plane = (long long)rows * cols;
@@ -279,6 +281,36 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
     phase_tail_finish_kernel<<<fgrid, 256, 0, stream>>>(out, (const double*)workspace, ntiles, plane);
     MM_LAUNCH_OK();
   }
+  return MIMAMO_OK;
+}
+
+// (re, im) -> (atan2(im, re), sqrt(re^2 + im^2) + 1e-10) in place, once per DISTINCT frame -- the same fp32 operations
+// the tail would otherwise repeat for each of the 13 windows a frame belongs to (bit-identical results).
+// frames whose root is another frame (window-batch path) hold no coefficients and are skipped.
+__global__ void __launch_bounds__(256)
+coeff_to_polar_kernel(float2* __restrict__ coeff, long long n_frames, int T, int nb, long long plane, const int* __restrict__ root) {
+  const long long f = blockIdx.x;
+  if (root != nullptr && root[f] != (int)f) return;
+  const long long w = f / T;
+  const int t = (int)(f - w * T);
+  for (int b = 0; b < nb; ++b) {
+    float2* p = coeff + (((size_t)w * nb + b) * T + t) * plane;
+    for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.y * blockDim.x) {
+      const float2 v = p[i];
+      float2 o;
+      o.x = atan2f(v.y, v.x);
+      o.y = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+      p[i] = o;
+    }
+  }
+}
+
+int coeff_to_polar_launch(float* coeff, long long n_frames, int T, int nb, int rows, int cols, const int* root, cudaStream_t stream) {
+  if (n_frames == 0) return MIMAMO_OK;
+  const long long plane = (long long)rows * cols;
+  dim3 grid((unsigned)n_frames, (unsigned)((plane + 1023) / 1024 > 8 ? 8 : (plane + 1023) / 1024));
+  coeff_to_polar_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float2*>(coeff), n_frames, T, nb, plane, root);
+  MM_LAUNCH_OK();
   return MIMAMO_OK;
 }
 
@@ -407,9 +439,12 @@ extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames
   const size_t idx2 = 2 * align_up((size_t)n_frames * sizeof(int), 256);
   int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, (char*)workspace + toff, total - toff - idx2, st);
   if (rc) return rc;
+  const int polar = root != nullptr ? 1 : 0;                // with de-duplication every frame is read through root[]
   for (int i = 0; i < nl; ++i) {
+    if (polar) rc = coeff_to_polar_launch(cptr[i], n_frames, T, nb, crops[i], crops[i], root, st);
+    if (rc) return rc;
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
-                              workspace_bytes - toff - 2 * align_up((size_t)n_frames * sizeof(int), 256), st, root, nb);
+                              workspace_bytes - toff - 2 * align_up((size_t)n_frames * sizeof(int), 256), st, root, nb, 0, polar);
     if (rc) return rc;
   }
   return MIMAMO_OK;
@@ -464,8 +499,10 @@ extern "C" int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float
   int rc = pyr_build_launch(plan, frames, n_frames, 1, cptr, nullptr, (char*)workspace + toff, total - toff, st);
   if (rc) return rc;
   for (int i = 0; i < nl; ++i) {
+    rc = coeff_to_polar_launch(cptr[i], n_frames, 1, nb, crops[i], crops[i], nullptr, st);
+    if (rc) return rc;
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
-                              total - toff, st, window_index, nb, 1);
+                              total - toff, st, window_index, nb, 1, 1);
     if (rc) return rc;
   }
   return MIMAMO_OK;
