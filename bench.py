@@ -202,8 +202,9 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local)                               # rank 0 samples its own GPU (one nvidia-smi poller per job, not per rank)
+    if rank == 0:
+        sampler.start()
     lib = _native.lib()
     lib.mimamo_profile_gemm(1)
     launches0 = _native.launch_count()
@@ -259,7 +260,8 @@ def main():
                         "unit": UNIT, "steps": n_f, "h2d_bytes_per_step": world * (gray_h.numel() + rgb_h.numel()) * 4}
         del gray_d, rgb_d
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     value = world * WINDOWS * args.steps / (ms / 1e3)
     e2e_value = world * WINDOWS * args.steps / (e2e_ms / 1e3)

@@ -34,6 +34,15 @@ struct TailGeom {
   int trp, tcp, rin, cin;
 };
 
+// (i / d, i % d) kept incrementally while i advances by a fixed stride: the tail's loops index small 2-D tiles whose
+// widths are run-time values, and a 32-bit division (~20 instructions) per element was a quarter of all instructions
+// issued (ncu source view: the kernel is issue-bound at 69 % issue-slot utilisation).
+struct DivMod {
+  int q, r;
+  __device__ __forceinline__ void init(int i, int d) { q = i / d; r = i - q * d; }
+  __device__ __forceinline__ void step(int sq, int sr, int d) { q += sq; r += sr; if (r >= d) { r -= d; ++q; } }
+};
+
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -50,7 +59,7 @@ __device__ __forceinline__ float unwrap_correction(float dd) {
   return corr;
 }
 
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreads, 2)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
                   const TailGeom g, const int* __restrict__ root, int nb, int coeff_T, int polar) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -89,6 +98,13 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
 #pragma unroll
   for (int d = 0; d < kTaps; ++d) gk[d] = c_gauss[d];
   __syncthreads();
+  // the (row, column) advance of one stride of the four strided loops below (block-uniform)
+  const int nthr = blockDim.x;
+  const int groups = tcp >> 2;
+  const int a_sq = nthr / (cw > 0 ? cw : 1), a_sr = nthr % (cw > 0 ? cw : 1);
+  const int b_sq = nthr / groups, b_sr = nthr % groups;
+  const int c_sq = nthr / tcp, c_sr = nthr % tcp;
+  const int w_sq = nthr / tw, w_sr = nthr % tw;
 
   for (int t = 0; t < g.T; ++t) {
     long long slot = ((size_t)map * g.T + t);
@@ -100,6 +116,8 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
     }
     const float2* src = reinterpret_cast<const float2*>(coeff) + (size_t)slot * plane;
     // (A) phase, magnitude, unwrap over time; loads are issued four at a time for memory-level parallelism
+    DivMod ia;
+    ia.init(threadIdx.x, cw > 0 ? cw : 1);
     for (int i0 = threadIdx.x; i0 < n_clip; i0 += 4 * blockDim.x) {
       float2 v[4];
       int cell[4];
@@ -108,10 +126,11 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
         const int i = i0 + u * blockDim.x;
         cell[u] = -1;
         if (i < n_clip) {
-          const int ry = ry0 + i / cw, rx = rx0 + i % cw;
+          const int ry = ry0 + ia.q, rx = rx0 + ia.r;
           cell[u] = ry * cin + rx;
           v[u] = __ldg(src + (size_t)(y0 - kHalo + ry) * g.cols + (x0 - kHalo + rx));
         }
+        ia.step(a_sq, a_sr, cw);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -134,9 +153,10 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
     __syncthreads();
     // (B) row pass: each thread produces 4 adjacent outputs of one row from 16 loaded inputs
     {
-      const int groups = tcp >> 2;
-      for (int i = threadIdx.x; i < rin * groups; i += blockDim.x) {
-        const int ry = i / groups, xg = (i - ry * groups) << 2;
+      DivMod ib;
+      ib.init(threadIdx.x, groups);
+      for (int i = threadIdx.x; i < rin * groups; i += blockDim.x, ib.step(b_sq, b_sr, groups)) {
+        const int ry = ib.q, xg = ib.r << 2;
         const float4* pa = reinterpret_cast<const float4*>(mp + ry * cin + xg);
         const float4* pb = reinterpret_cast<const float4*>(mg + ry * cin + xg);
         float a[16], b[16];
@@ -160,8 +180,10 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
     double part = 0.0;
     {
       const int ygroups = trp >> 2;
-      for (int i = threadIdx.x; i < ygroups * tcp; i += blockDim.x) {
-        const int yg = (i / tcp) << 2, x = i % tcp;
+      DivMod ic;
+      ic.init(threadIdx.x, tcp);
+      for (int i = threadIdx.x; i < ygroups * tcp; i += blockDim.x, ic.step(c_sq, c_sr, tcp)) {
+        const int yg = ic.q << 2, x = ic.r;
         float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int r = 0; r < 14; ++r) {
@@ -202,8 +224,10 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       const float mean = single ? mean_s : 0.f;
       const float lim = 15.7079632679489656f;                    // 5*pi
       float* dst = out + ((size_t)map * (g.T - 1) + (t - 1)) * plane;
-      for (int i = threadIdx.x; i < th * tw; i += blockDim.x) {
-        const int y = i / tw, x = i - y * tw;
+      DivMod iw;
+      iw.init(threadIdx.x, tw);
+      for (int i = threadIdx.x; i < th * tw; i += blockDim.x, iw.step(w_sq, w_sr, tw)) {
+        const int y = iw.q, x = iw.r;
         float v = delta[y * tcp + x];
         if (single) v = fminf(fmaxf(__fsub_rn(v, mean), -lim), lim);
         dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
