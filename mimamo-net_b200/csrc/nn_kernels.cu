@@ -398,7 +398,8 @@ int linear_forward(const LinearLayer& L, const float* a, int lda, int M, float* 
 // so the recurrence runs over dim 0 (snippets) and the 64 frames are independent batch rows
 // (SURVEY.md section 0.2).  One CTA owns kGruRows batch rows of one direction for the whole
 // sequence (persistent over time); thread j owns hidden unit j.  Gate order r, z, n as in torch.
-constexpr int kGruRows = 4;
+constexpr int kGruRows = 1;       // one batch row per CTA: 64 rows x 2 directions = 128 CTAs fill the GPU and the per-step matvec is 4x shorter
+                                  // than with 4 rows per CTA (the recurrence is a chain of 2 x S dependent steps: latency is what counts)
 constexpr int kGruHd = 128, kGruG = 3 * kGruHd;
 constexpr int kGruSmem = (kGruHd * kGruG + 2 * kGruRows * kGruHd + kGruRows * kGruG) * (int)sizeof(float);
 
@@ -426,6 +427,20 @@ gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, cons
   int cur = 0;
   for (int step = 0; step < S; ++step) {
     const int s = dir == 0 ? step : S - 1 - step;
+    // this step's input projections are fetched before the matvec so that their latency hides behind it
+    float xr[2], xz[2], xn[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * (int)blockDim.x;
+      xr[u] = xz[u] = xn[u] = 0.f;
+      if (i < R * Hd) {
+        const int r = i / Hd, j = i - r * Hd;
+        if (row0 + r < Bt) {
+          const float* xp = xproj + (((size_t)s * Bt + row0 + r) * 2 + dir) * G;
+          xr[u] = __ldg(xp + j); xz[u] = __ldg(xp + Hd + j); xn[u] = __ldg(xp + 2 * Hd + j);
+        }
+      }
+    }
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = bias;
@@ -444,15 +459,18 @@ gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, cons
     for (int r = 0; r < R; ++r) gh[r * G + g] = acc[r];
     __syncthreads();
     float* hn_buf = h + (cur ^ 1) * R * Hd;
-    for (int i = threadIdx.x; i < R * Hd; i += blockDim.x) {
+    static_assert(R * Hd <= 2 * G, "two gate items per thread at most");
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = threadIdx.x + u * (int)blockDim.x;
+      if (i >= R * Hd) break;
       const int r = i / Hd, j = i - r * Hd;
       const int row = row0 + r;
       float hn = 0.f;
       if (row < Bt) {
-        const float* xp = xproj + (((size_t)s * Bt + row) * 2 + dir) * G;
-        const float rg = 1.f / (1.f + expf(-(xp[j] + gh[r * G + j])));
-        const float zg = 1.f / (1.f + expf(-(xp[Hd + j] + gh[r * G + Hd + j])));
-        const float ng = tanhf(xp[2 * Hd + j] + rg * gh[r * G + 2 * Hd + j]);
+        const float rg = 1.f / (1.f + expf(-(xr[u] + gh[r * G + j])));
+        const float zg = 1.f / (1.f + expf(-(xz[u] + gh[r * G + Hd + j])));
+        const float ng = tanhf(xn[u] + rg * gh[r * G + 2 * Hd + j]);
         hn = (1.f - zg) * ng + zg * hc[r * Hd + j];
         y[((size_t)s * Bt + row) * (2 * Hd) + dir * Hd + j] = hn;
       }
