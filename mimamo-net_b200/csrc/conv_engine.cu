@@ -52,6 +52,8 @@ struct ConvParams {
   int ldc, ld_res;
   int relu;
   int debug;                 // timing experiments only (MIMAMO_DEBUG): 1 = epilogue skips math+store, 2 = line kernel issues 4 of 16 UMMAs
+  int pair;                  // conv_gemm_kernel launched as 2-CTA clusters: the two CTAs work on adjacent M tiles of the same N tile and
+                             // each fetches half of every weight box, multicast into both shared memories (halves the L2->SM weight traffic)
   int store_mode;            // epilogue TMA store granularity: 0 = per warp (32 rows, flat layers), 1 = per column group, 2 = whole tile
   int resident_w;            // halo kernel: the whole 3x3 weight set stays in shared memory (Cin_p == 64, 9 taps <= kBStages boxes)
 };
@@ -276,6 +278,19 @@ __device__ __forceinline__ void tma_store_2d(uint64_t map, uint32_t src, int c0,
 __device__ __forceinline__ void tma_store_4d(uint64_t map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// ---- 2-CTA cluster helpers (pair mode of conv_gemm_kernel) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2d_multicast_u32(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void commit_multicast_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -296,7 +311,7 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 template <int BLOCK_N, bool BF16, bool HAS_RES, int EPI_BUFS>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                               int num_tiles) {
+                                               int num_tiles, int tile0, int tile_stride, int m_shift = 0, int m_rank = 0) {
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per tile (64-wide tiles: 2)
@@ -327,9 +342,10 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
 
     auto issue_residual = [&](int q) {                        // chunk q of this warp's flattened (tile, chunk) list
       if (HAS_RES) {
-        const int tile = blockIdx.x + (q / CPW) * gridDim.x;
+        const int tile = tile0 + (q / CPW) * tile_stride;
         if (tile < num_tiles) {
-          const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+          const int m_lin = tile / p.n_tiles, n_tile = tile - m_lin * p.n_tiles;
+          const int m_tile = (m_lin << m_shift) + m_rank;
           const int ch = n_tile * BLOCK_N + half * COLS + (q % CPW) * 32 + pair * 8;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -348,10 +364,11 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
     for (int q = 0; q < kResDepth; ++q) issue_residual(q);
 
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int m_lin = tile / p.n_tiles, n_tile = tile - m_lin * p.n_tiles;
+      const int m_tile = (m_lin << m_shift) + m_rank;
       const int n0 = n_tile * BLOCK_N + half * COLS;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -465,16 +482,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    // pair mode: a stage is reusable once BOTH CTAs' MMAs have read it (each CTA's producer also writes the peer's stage)
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], p.pair ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();                            // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // tile list of this CTA: plain = tiles blockIdx.x, +gridDim.x, ...; pair = tiles of (M-tile pair, N tile), this CTA taking
+  // M tile 2 * pair + rank (an M tile past the end is computed on zero-filled rows and clipped by the TMA store)
+  const uint32_t rank = p.pair ? cluster_ctarank() : 0u;
+  const int m_shift = p.pair ? 1 : 0;
+  const int num_tiles = p.pair ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int tile0 = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   // The issue warps execute a strictly serial instruction stream: at ~5 cycles per dependent
   // instruction their loop length, not TMA or the tensor pipe, bounded the first versions of this
@@ -485,6 +510,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = elect_one();
     const uint32_t tx_bytes = (uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes;
     const int n_tiles = p.n_tiles, mode = p.mode, cin_blocks = p.cin_blocks, taps_w = p.taps_w;
+    const bool pair = p.pair != 0;
     const int taps_h = p.num_k_blocks / (cin_blocks * taps_w);
     const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
     const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
@@ -493,8 +519,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0; uint32_t parity = 1;                        // producer waits on empty with parity phase ^ 1
     uint32_t dA = sA0, dB = sB0, fb = full0, eb = empty0;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+      const int m_lin = tile / n_tiles, n_tile = tile - m_lin * n_tiles;
+      const int m_tile = (m_lin << m_shift) + (int)rank;
       const int n0 = n_tile * BLOCK_N;
       int c1 = 0, c2 = 0, c3 = 0;
       if (mode == 0) {
@@ -518,7 +545,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               bar_expect_tx_u32(fb, tx_bytes);
               if (mode == 0) tma2d_u32(dA, mapA, fb, cb * kBlockK, c1);
               else tma4d_u32(dA, mapA, fb, cb * kBlockK, c1 + kw, c2 + kh, c3);
-              tma2d_u32(dB, mapB, fb, kcol, n0);
+              if (pair) tma2d_multicast_u32(dB + rank * (Cfg::kBStageBytes / 2), mapB, fb, kcol, n0 + (int)rank * (BLOCK_N / 2), (uint16_t)3);
+              else tma2d_u32(dB, mapB, fb, kcol, n0);
             }
             if (++stage == STAGES) { stage = 0; parity ^= 1; dA = sA0; dB = sB0; fb = full0; eb = empty0; }
             else { dA += kAStageBytes; dB += Cfg::kBStageBytes; fb += 8; eb += 8; }
@@ -537,8 +565,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int stage = 0; uint32_t parity = 0;
     uint32_t a_lo = a_lo0, b_lo = b_lo0, fb = full0, eb = empty0;
     int local = 0;
+    const bool pair = p.pair != 0;
 #pragma unroll 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++local) {
       const uint32_t acc = local & 1;
       bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -549,7 +578,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (leader) {
           umma_kblock(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
-          commit_u32(eb);                                      // frees the smem stage when the MMAs retire
+          if (pair) commit_multicast_u32(eb, (uint16_t)3);     // frees the stage in both CTAs when these MMAs retire
+          else commit_u32(eb);                                 // frees the smem stage when the MMAs retire
           if (kb == nkb - 1) commit_u32(tfull0 + acc * 8);
         }
         if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
@@ -557,10 +587,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0, tile_stride,
+                                                          m_shift, (int)rank);
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();                            // the peer may still signal this CTA's barriers until it is done too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -723,7 +755,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles);
+    epilogue_warps<BLOCK_N, BF16, false, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles, blockIdx.x, gridDim.x);
   }
   tc_fence_before();
   __syncthreads();
@@ -897,7 +929,7 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (!POOL) {
-    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles);
+    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles, blockIdx.x, gridDim.x);
   } else {
     // ---- fused BN + ReLU + max pool epilogue: all 16 warps, thread = output column dw, 16 channels.  (With 8 warps
     // of 32 channels the epilogue ran at 0.86 us per line against 0.64 us of load + MMA: two warps per scheduler
@@ -1076,7 +1108,20 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
     g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * BLOCK_N * (double)p.num_k_blocks * kBlockK;
     MM_CUDA(cudaEventRecord(e0, stream));
   }
-  conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
+  if (p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);      // whole clusters only; pair tiles are distributed over grid / 2 clusters
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, a, b, o, p));
+  } else {
+    conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
+  }
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
@@ -1209,6 +1254,16 @@ void conv_layer_free(ConvLayer& L) {
   L.w_dev = nullptr; L.scale_dev = L.shift_dev = nullptr;
 }
 
+// Pair mode (2-CTA clusters, multicast weight boxes) pays where the weight tile dominates the bytes a tile pulls
+// through L2 -> SM: 256-wide tiles with K >= 256 and enough M tiles to keep every cluster busy (measured: -3 % on the stage-4
+// 3x3 and increase layers; those layers turned out not to be weight-traffic-bound).  MIMAMO_PAIR=0 disables, 2 forces (tests).
+static bool pair_wanted(int block_n, int num_k_blocks, int m_tiles) {
+  const char* e = getenv("MIMAMO_PAIR");                     // read per call: the tests force pair mode on small shapes ("2")
+  const int on = e ? atoi(e) : 1;
+  if (on == 2) return block_n == 256 && m_tiles >= 1;
+  return on == 1 && block_n == 256 && num_k_blocks >= 4 && m_tiles >= num_sms();
+}
+
 static int weight_map(const ConvLayer& L, CUtensorMap* map, int block_n) {
   const uint64_t K = (uint64_t)L.ksize * L.ksize * L.Cin_p;
   const uint64_t dims[2] = {K, (uint64_t)L.Cout};
@@ -1246,10 +1301,12 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, residual, ld_res));
-  if (rc) return rc;
+  const int bn = fill_common(p, L, out, ldc, residual, ld_res);
   p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.pair = pair_wanted(bn, p.num_k_blocks, p.m_tiles) ? 1 : 0;
+  rc = weight_map(L, &mb, p.pair ? bn / 2 : bn);              // pair mode: each CTA fetches half of the N rows of a weight box
+  if (rc) return rc;
   CUtensorMap mo;
   p.store_mode = store_mode_setting(0);
   rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr), p.store_mode == 0 ? 32 : kBlockM);
@@ -1336,8 +1393,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  rc = weight_map(L, &mb, fill_common(p, L, out, ldc, residual, ld_res));
-  if (rc) return rc;
+  const int bn_eff = fill_common(p, L, out, ldc, residual, ld_res);
   p.mode = 1;
   p.Wo = Wo; p.Ho = Ho; p.Nimg = B;
   p.bw = best_bw; p.bh = best_bh; p.bn = best_bn;
@@ -1345,6 +1401,9 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.tiles_h = (Ho + best_bh - 1) / best_bh;
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
+  p.pair = pair_wanted(bn_eff, p.num_k_blocks, p.m_tiles) ? 1 : 0;
+  rc = weight_map(L, &mb, p.pair ? bn_eff / 2 : bn_eff);
+  if (rc) return rc;
   CUtensorMap mo;
   p.store_mode = store_mode_setting(L.ksize == 1 ? 1 : 2);
   rc = out_map_spatial(&mo, L.elem, out, ldc, L.Cout, Wo, Ho, B, best_bw, best_bh, best_bn, effective_block_n(L, residual != nullptr));

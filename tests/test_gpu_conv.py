@@ -28,9 +28,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("pair", ["1", "2"])              # "2": force the 2-CTA cluster / multicast-weights mode on every 256-wide layer
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c))
-def test_conv_engine(cuda, case):
+def test_conv_engine(cuda, case, pair, monkeypatch):
     import _native
+    if pair == "2" and case[4] % 256 != 0:
+        pytest.skip("pair mode only exists for 256-wide tiles")
+    monkeypatch.setenv("MIMAMO_PAIR", pair)
     B, H, W, Cin, Cout, k, s, p, relu, use_res = case
     gen = torch.Generator().manual_seed(sum(case[:8]))
     x = torch.randn(B, H, W, Cin, generator=gen).to(torch.bfloat16)
