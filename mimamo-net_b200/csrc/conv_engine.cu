@@ -291,6 +291,55 @@ __device__ __forceinline__ void tma2d_multicast_u32(uint32_t dst, uint64_t map, 
 __device__ __forceinline__ void commit_multicast_u32(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- cta_group::2 (2-SM UMMA) helpers ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_rank) {       // same offset in the peer's shared memory
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA, the bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma2d_2sm_u32(uint32_t dst, uint64_t map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma4d_2sm_u32(uint32_t dst, uint64_t map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void commit2_multicast_u32(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+// Four K=16 UMMAs of one 64-wide K block issued for BOTH CTAs of the pair (M = 256: 128 rows of A from each CTA's shared
+// memory, N = 256: 128 rows of B from each), accumulating into the same TMEM columns of both CTAs.
+__device__ __forceinline__ void umma2_kblock(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "add.u32 al, %1, 2;\n add.u32 bl, %2, 2;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+      "add.u32 al, %1, 4;\n add.u32 bl, %2, 4;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+      "add.u32 al, %1, 6;\n add.u32 bl, %2, 6;\n mov.b64 da, {al, %5};\n mov.b64 db, {bl, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -311,7 +360,8 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 template <int BLOCK_N, bool BF16, bool HAS_RES, int EPI_BUFS>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                               int num_tiles, int tile0, int tile_stride, int m_shift = 0, int m_rank = 0) {
+                                               int num_tiles, int tile0, int tile_stride, int m_shift = 0, int m_rank = 0,
+                                               uint32_t tmem_empty_leader = 0 /* cta_group::2: shared::cluster address of the leader's tmem_empty[0] */) {
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per tile (64-wide tiles: 2)
@@ -379,7 +429,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       if (issuer) { if (EPI_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
       sync_store_group();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
-      if (p.debug & 1) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
+      if ((p.debug & 1) && !tmem_empty_leader) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
         uint32_t v[32];
@@ -428,7 +478,10 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       // accumulator fully read: hand the TMEM buffer back before the store is even issued
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (tmem_empty_leader) mbar_arrive_cluster_u32(tmem_empty_leader + acc * 8);   // the pair's MMAs are issued by the leader CTA
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       fence_proxy_async_smem();                                // generic-proxy writes -> visible to the TMA engine
       sync_store_group();
       if (issuer) {
@@ -596,6 +649,163 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_gemm2_kernel: the same implicit GEMM on CTA PAIRS with tcgen05.mma.cta_group::2.
+//
+// K-heavy 256-wide layers (stage 4/5 of ResNet50) pull 48 KB per 512 MMA cycles into every SM (16 KB of activations +
+// 32 KB of weights per K block) and stall on that ingress (tensor pipe 50-60 % active, DRAM < 50 %).  With the 2-SM UMMA
+// a pair of CTAs on adjacent M tiles computes a 256 x 256 tile: each CTA stages its own 128 activation rows and only
+// HALF of the weight rows (16 KB); the tensor cores of both SMs read both halves.  Per-SM ingress drops to 32 KB per
+// K block and the freed shared memory deepens the ring (5 stages instead of 3; 3 instead of 2 with a residual).
+// Roles: both CTAs run a producer warp (their TMA bytes are credited to the LEADER's full barrier) and the 16
+// epilogue warps (each CTA reads its own TMEM lanes); only the leader's MMA warp issues, and its tcgen05.commit is
+// multicast to both CTAs' empty / tmem_full barriers; both epilogues arrive at the leader's tmem_empty barrier.
+// ---------------------------------------------------------------------------------------
+template <int BLOCK_N, bool HAS_RES>
+struct Gemm2Cfg {
+  static constexpr int kBStageBytes = (BLOCK_N / 2) * kBlockK * 2;
+  static constexpr int kEpiBufs = 1;
+  static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
+  static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;
+  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
+  static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 256 + 1024;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+};
+
+template <int BLOCK_N, bool BF16, bool HAS_RES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
+  using Cfg = Gemm2Cfg<BLOCK_N, HAS_RES>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStageBytes;
+  uint8_t* sEpi = sB + STAGES * Cfg::kBStageBytes;
+  uint8_t* sRes = sEpi + Cfg::kEpiBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sRes + Cfg::kResBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  constexpr int kEpiArrivals = 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiArrivals); }   // both CTAs' epilogue warps
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = ((p.m_tiles + 1) >> 1) * p.n_tiles;  // (M-tile pair, N tile); this CTA owns M tile 2 * pair + rank
+  const int tile0 = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------------------
+    const bool leader = elect_one();
+    const uint32_t pair_tx = 2u * ((uint32_t)p.a_rows * (kBlockK * 2) + Cfg::kBStageBytes);
+    const int n_tiles = p.n_tiles, mode = p.mode, cin_blocks = p.cin_blocks, taps_w = p.taps_w;
+    const int taps_h = p.num_k_blocks / (cin_blocks * taps_w);
+    const int tiles_w = p.tiles_w, tiles_h = p.tiles_h;
+    const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t lfull0 = mapa_u32(full0, 0);              // the leader's full barriers (own ones when rank == 0)
+    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    int stage = 0; uint32_t parity = 1;
+    uint32_t dA = sA0, dB = sB0, fb = full0, lfb = lfull0, eb = empty0;
+#pragma unroll 1
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+      const int m_lin = tile / n_tiles, n_tile = tile - m_lin * n_tiles;
+      const int m_tile = (m_lin << 1) + (int)rank;
+      const int n0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);     // this CTA's half of the weight rows
+      int c1 = 0, c2 = 0, c3 = 0;
+      if (mode == 0) {
+        c1 = m_tile * kBlockM;
+      } else {
+        const int tw = m_tile % tiles_w, rest = m_tile / tiles_w;
+        const int th = rest % tiles_h, tn = rest / tiles_h;
+        c1 = tw * step_w - pad;
+        c2 = th * step_h - pad;
+        c3 = tn * bn;
+      }
+      int kcol = 0;
+#pragma unroll 1
+      for (int kh = 0; kh < taps_h; ++kh) {
+#pragma unroll 1
+        for (int kw = 0; kw < taps_w; ++kw) {
+#pragma unroll 1
+          for (int cb = 0; cb < cin_blocks; ++cb, kcol += kBlockK) {
+            bar_wait_u32(eb, parity);
+            if (leader) {
+              if (rank == 0) bar_expect_tx_u32(fb, pair_tx);   // bytes of BOTH CTAs' boxes
+              if (mode == 0) tma2d_2sm_u32(dA, mapA, lfb, cb * kBlockK, c1);
+              else tma4d_2sm_u32(dA, mapA, lfb, cb * kBlockK, c1 + kw, c2 + kh, c3);
+              tma2d_2sm_u32(dB, mapB, lfb, kcol, n0);
+            }
+            if (++stage == STAGES) { stage = 0; parity ^= 1; dA = sA0; dB = sB0; fb = full0; lfb = lfull0; eb = empty0; }
+            else { dA += kAStageBytes; dB += Cfg::kBStageBytes; fb += 8; lfb += 8; eb += 8; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) ---------------------------------
+    if (rank == 0) {
+      const bool leader = elect_one();
+      const int nkb = p.num_k_blocks;
+      const uint32_t idesc = p.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+      int stage = 0; uint32_t parity = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0, fb = full0, eb = empty0;
+      int local = 0;
+#pragma unroll 1
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++local) {
+        const uint32_t acc = local & 1;
+        bar_wait_u32(tempty0 + acc * 8, ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          bar_wait_u32(fb, parity);
+          tc_fence_after();
+          if (leader) {
+            umma2_kblock(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+            commit2_multicast_u32(eb, (uint16_t)3);            // frees the stage in both CTAs
+            if (kb == nkb - 1) commit2_multicast_u32(tfull0 + acc * 8, (uint16_t)3);
+          }
+          if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
+          else { a_lo += kAStageBytes >> 4; b_lo += Cfg::kBStageBytes >> 4; fb += 8; eb += 8; }
+        }
+      }
+    }
+  } else {
+    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0,
+                                                          tile_stride, 1, (int)rank, mapa_u32(smem_u32(tmem_empty), 0));
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                        // neither CTA may retire while the other still signals / reads it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -1067,6 +1277,11 @@ static uint32_t make_idesc(int block_n, ElemType elem) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
 }
 
+static uint32_t make_idesc2(int block_n, ElemType elem) {    // cta_group::2: M = 256 across the CTA pair
+  const uint32_t fmt = elem == kBF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
 int out_size(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
 static int num_sms() {
@@ -1127,6 +1342,45 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   return MIMAMO_OK;
 }
 
+// cta_group::2 launch (256-wide tiles only): clusters of two CTAs, M = 256 instruction descriptor
+template <bool BF16, bool HAS_RES>
+static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<256, HAS_RES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<256, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t a0, a1;
+      MM_CUDA(cudaEventCreate(&a0));
+      MM_CUDA(cudaEventCreate(&a1));
+      g_prof_events.emplace_back(a0, a1);
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * (double)p.n_tiles * 256 * (double)p.num_k_blocks * kBlockK;
+    MM_CUDA(cudaEventRecord(e0, stream));
+  }
+  cudaLaunchConfig_t cfg = {};
+  const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int max_pairs = num_sms() / 2;
+  cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<256, BF16, HAS_RES>, a, b, o, p));
+  count_launch();
+  if (e1) MM_CUDA(cudaEventRecord(e1, stream));
+  return MIMAMO_OK;
+}
+
 template <int BLOCK_N>
 static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
   if (bf) return res ? launch_cfg<BLOCK_N, true, true>(a, b, o, p, s) : launch_cfg<BLOCK_N, true, false>(a, b, o, p, s);
@@ -1178,6 +1432,10 @@ static int store_mode_setting(int kind) {
 
 static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
   const bool bf = L.elem == kBF16, res = p.residual != nullptr;
+  if (p.pair == 2) {
+    if (bf) return res ? launch_cfg2<true, true>(a, b, o, p, s) : launch_cfg2<true, false>(a, b, o, p, s);
+    return res ? launch_cfg2<false, true>(a, b, o, p, s) : launch_cfg2<false, false>(a, b, o, p, s);
+  }
   switch (effective_block_n(L, res)) {
     case 64:  return launch_n<64>(bf, res, a, b, o, p, s);
     case 128: return launch_n<128>(bf, res, a, b, o, p, s);
@@ -1257,11 +1515,23 @@ void conv_layer_free(ConvLayer& L) {
 // Pair mode (2-CTA clusters, multicast weight boxes) pays where the weight tile dominates the bytes a tile pulls
 // through L2 -> SM: 256-wide tiles with K >= 256 and enough M tiles to keep every cluster busy (measured: -3 % on the stage-4
 // 3x3 and increase layers; those layers turned out not to be weight-traffic-bound).  MIMAMO_PAIR=0 disables, 2 forces (tests).
-static bool pair_wanted(int block_n, int num_k_blocks, int m_tiles) {
-  const char* e = getenv("MIMAMO_PAIR");                     // read per call: the tests force pair mode on small shapes ("2")
-  const int on = e ? atoi(e) : 1;
-  if (on == 2) return block_n == 256 && m_tiles >= 1;
-  return on == 1 && block_n == 256 && num_k_blocks >= 4 && m_tiles >= num_sms();
+// Returns 0 (single CTAs), 1 (pair mode, multicast weights) or 2 (cta_group::2 UMMA) for a 256-wide layer.
+// Measured per 2048 images (profiles/layers_r1_pair_modes.txt; modes 0 / 1 / 2): stage-4 reduce 212 / 215 / 184 us,
+// stage-4 3x3 417 / 412 / 367, stage-5 reduce 184 / 184 / 152, stage-5 3x3 398 / 392 / 357, stage-5 proj 433 / 413 / 357,
+// stage-5 increase 283 / 275 / 247 -- but stage-4 increase 375 / 365 / 420 and the strided stage-4 proj 492 / 482 / 507:
+// with few K blocks per tile the layer is epilogue-bound and coupling the two CTAs' epilogues to one MMA issuer costs
+// more than the halved weight ingress saves.  Hence: cta_group::2 from 16 K blocks (8 on flat layers), multicast pairs
+// from 4.  MIMAMO_PAIR = "<mode><force>": first digit caps the mode (default 2), a second digit 1 forces exactly that
+// mode on every 256-wide layer (tests).
+static int pair_wanted(int block_n, int num_k_blocks, int m_tiles, bool flat) {
+  const char* e = getenv("MIMAMO_PAIR");
+  const int cap = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  const bool force = e && e[0] && e[1] == '1';
+  if (cap == 0 || block_n != 256) return 0;
+  if (force) return cap;
+  if (m_tiles < num_sms() || num_k_blocks < 4) return 0;
+  const int want = (num_k_blocks >= 16 || (flat && num_k_blocks >= 8)) ? 2 : 1;
+  return want < cap ? want : cap;
 }
 
 static int weight_map(const ConvLayer& L, CUtensorMap* map, int block_n) {
@@ -1304,7 +1574,8 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   const int bn = fill_common(p, L, out, ldc, residual, ld_res);
   p.mode = 0; p.M_total = M; p.a_rows = kBlockM;
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
-  p.pair = pair_wanted(bn, p.num_k_blocks, p.m_tiles) ? 1 : 0;
+  p.pair = pair_wanted(bn, p.num_k_blocks, p.m_tiles, true);
+  if (p.pair == 2) p.idesc = make_idesc2(bn, L.elem);
   rc = weight_map(L, &mb, p.pair ? bn / 2 : bn);              // pair mode: each CTA fetches half of the N rows of a weight box
   if (rc) return rc;
   CUtensorMap mo;
@@ -1401,7 +1672,8 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.tiles_h = (Ho + best_bh - 1) / best_bh;
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
-  p.pair = pair_wanted(bn_eff, p.num_k_blocks, p.m_tiles) ? 1 : 0;
+  p.pair = pair_wanted(bn_eff, p.num_k_blocks, p.m_tiles, false);
+  if (p.pair == 2) p.idesc = make_idesc2(bn_eff, L.elem);
   rc = weight_map(L, &mb, p.pair ? bn_eff / 2 : bn_eff);
   if (rc) return rc;
   CUtensorMap mo;

@@ -28,11 +28,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("pair", ["1", "2"])              # "2": force the 2-CTA cluster / multicast-weights mode on every 256-wide layer
+# MIMAMO_PAIR "<mode><force>": "0" single CTAs; "11" forces 2-CTA clusters with multicast weight boxes on every 256-wide
+# layer; "21" forces the cta_group::2 UMMA kernel (shapes this small would not select them on their own)
+@pytest.mark.parametrize("pair", ["0", "11", "21"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c))
 def test_conv_engine(cuda, case, pair, monkeypatch):
     import _native
-    if pair == "2" and case[4] % 256 != 0:
+    if pair != "0" and case[4] % 256 != 0:
         pytest.skip("pair mode only exists for 256-wide tiles")
     monkeypatch.setenv("MIMAMO_PAIR", pair)
     B, H, W, Cin, Cout, k, s, p, relu, use_res = case
