@@ -1325,7 +1325,10 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   }
   if (p.pair) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);      // whole clusters only; pair tiles are distributed over grid / 2 clusters
+    static int max_pairs = 0;
+    if (!max_pairs) max_pairs = max_pairs_for(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, Cfg::kSmemBytes);
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);   // whole, co-resident clusters only
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
@@ -1340,6 +1343,25 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
+}
+
+// Persistent 2-CTA-cluster kernels must not launch more clusters than can be co-resident (GPCs with an odd number of
+// free SMs cannot host a pair): ask the occupancy calculator once per kernel.
+template <typename Kernel>
+static int max_pairs_for(Kernel kernel, size_t smem_bytes) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_sms() & ~1), 1, 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / 2; }
+  const int cap = num_sms() / 2;
+  if (getenv("MIMAMO_VERBOSE")) fprintf(stderr, "mimamo: %d co-resident 2-CTA clusters (of %d SM pairs), %zu B of shared memory per CTA\n", n, cap, smem_bytes);
+  return n < cap ? n : cap;
 }
 
 // cta_group::2 launch (256-wide tiles only): clusters of two CTAs, M = 256 instruction descriptor
@@ -1366,7 +1388,8 @@ static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   }
   cudaLaunchConfig_t cfg = {};
   const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  const int max_pairs = num_sms() / 2;
+  static int max_pairs = 0;
+  if (!max_pairs) max_pairs = max_pairs_for(conv_gemm2_kernel<256, BF16, HAS_RES>, Cfg::kSmemBytes);
   cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
