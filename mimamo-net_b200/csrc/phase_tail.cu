@@ -52,7 +52,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // operation order of api/utils/phase_utils.py:9-17 is reproduced so residues match bit for bit.
 __device__ __forceinline__ float unwrap_correction(float dd) {
   const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
-  float ddmod = __fsub_rn(fmodf(__fadd_rn(dd, PI_F), TWO_PI_F), PI_F);
+  // fmod(dd + pi, 2 pi) without the library loop: both phases come from atan2f, so x = dd + pi lies in [-pi, 3 pi];
+  // C fmod keeps the dividend's sign (x < 2 pi is returned unchanged) and for x in [2 pi, 3 pi] the remainder x - 2 pi
+  // is exact in fp32 (Sterbenz: y <= x <= 2 y), i.e. the single subtraction IS fmodf's result bit for bit.
+  const float x = __fadd_rn(dd, PI_F);
+  float ddmod = __fsub_rn(x >= TWO_PI_F ? __fsub_rn(x, TWO_PI_F) : x, PI_F);
   if (ddmod == -PI_F && dd > 0.f) ddmod = PI_F;
   float corr = __fsub_rn(ddmod, dd);
   if (fabsf(dd) < PI_F) corr = 0.f;
