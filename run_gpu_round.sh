@@ -1,5 +1,8 @@
 #!/bin/bash
-# One GPU round trip: GPU suites, the bench line, the ncu launch list of one quick step.
+# One GPU round trip (used through `gpurun -- ./run_gpu_round.sh`): GPU suites, the bench line, optionally the ncu
+# launch list of one quick step (NCU_LIST=1) and a --set full capture (NCU_FULL=<kernel regex>; keep the .ncu-rep small:
+# gpurun only copies back 64 MiB -- summarise on the box with tools_ncu_summary.py for anything bigger).
+# TESTS="..." selects test files, BENCH_ARGS extra bench.py flags.
 mkdir -p gpurun_out
 for f in ${TESTS:-test_gpu_preproc test_gpu_pyramid test_gpu_nets test_gpu_conv}; do
   timeout 900 python -m pytest tests/$f.py -q -m gpu -x -s > gpurun_out/$f.log 2>&1
