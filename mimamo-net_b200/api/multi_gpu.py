@@ -47,3 +47,16 @@ def gather_predictions(local_preds, n_videos_total, group=None):
         for i in range(hi - lo):
             out.append(everything[r * per_rank + i, :int(all_lens[r * per_rank + i])])
     return out
+
+
+def run_videos(tester, videos, group=None):
+    """BASELINE config 5: `videos` is the FULL list of videos (each uint8 (n_v, S, S, 3) aligned face crops, host or
+    device); every rank runs Tester.predict_frames on its contiguous block and the per-video (n_v, 2) predictions are
+    gathered once.  Returns the list for all videos on every rank; identical for any world size, because a video is
+    never split across ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(videos), rank, world)
+    device = torch.device('cuda', torch.cuda.current_device())
+    local = [tester.predict_frames(torch.as_tensor(v).to(device, non_blocking=True)) for v in videos[lo:hi]]
+    return gather_predictions(local, len(videos), group)

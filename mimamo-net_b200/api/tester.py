@@ -259,6 +259,47 @@ class Tester(object):
         return out.cpu() if to_host else out
 
 
+    # ------------------------------------------------------------------ B200 video path (uint8 in, DataFrame out)
+    def predict_frames(self, frames):
+        """One video's aligned face crops, uint8 (n, S, S, 3) on the GPU -> (n, 2) float32 CUDA predictions with
+        exactly the semantics of `test` (api/tester.py:53-121): 13-frame windows clamped to the VIDEO
+        (snippet_sampler.py:144-152), 64-frame snippets plus the overlapping tail snippet (:116-126), the video's
+        snippets forwarded as one batch of at most `batch_size` (the GRU runs over the snippets of a batch) and
+        later snippets overwriting the overlap when stitched (:104-118).  Every frame is preprocessed, transformed
+        and pushed through ResNet50 once, however many windows / snippets it belongs to."""
+        from sampler.snippet_sampler import snippet_ranges, window_index
+        n = frames.shape[0]
+        if n == 0:
+            raise ValueError("number of frames of video should not be zero.")
+        device = frames.device
+        with torch.no_grad():
+            pre = self.crop_preprocessor()
+            idx = window_index(0, n, n, self.num_phase).to(device=device, dtype=torch.int32)
+            diffs = self.phase_difference_extractor.phase_difference_indexed(pre.gray(frames), idx)
+            phase = [d.view(n, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+            feats = self.resnet50_extractor.features_from_crops(frames, pre)
+            ranges = snippet_ranges(n, self.length, self.stride)
+            out = torch.zeros((n, len(self.label_name)), dtype=torch.float32, device=device)
+            for b0 in range(0, len(ranges), self.batch_size):             # DataLoader batches, in order
+                batch = ranges[b0:b0 + self.batch_size]
+                rows = torch.cat([torch.arange(s, e, device=device) for s, e in batch])
+                L = batch[0][1] - batch[0][0]
+                p0 = phase[0].index_select(0, rows).view(len(batch), L, *phase[0].shape[1:])
+                p1 = phase[1].index_select(0, rows).view(len(batch), L, *phase[1].shape[1:])
+                pred = self.model([p0, p1], feats.index_select(0, rows).view(len(batch), L, -1))
+                for k, (s, e) in enumerate(batch):                        # in order: the tail snippet overwrites its overlap
+                    out[s:e] = pred[k]
+        return out
+
+    def test_frames(self, frames, video_name='video'):
+        """`test` without OpenFace / files: frames = decoded aligned crops of one video, uint8 (n, S, S, 3), host or
+        device.  Returns {video_name: DataFrame(columns=['valence', 'arousal'])} like the reference."""
+        import pandas as pd
+        frames = torch.as_tensor(frames)
+        pred = self.predict_frames(frames.to(get_device(), non_blocking=True))
+        return {video_name: pd.DataFrame(data=pred.cpu().numpy().astype(np.float64), columns=self.label_name)}
+
+
 def stitch_predictions(names, ranges, preds):
     """Per-video stitching of snippet predictions (api/tester.py:104-118): later snippets overwrite the
     overlap; asserts full coverage [0, max_len)."""

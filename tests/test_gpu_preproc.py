@@ -89,3 +89,41 @@ def test_infer_crops_matches_clip_path_and_oracle(cuda):
     assert out.shape == (B, Fr, 2) and err < 3e-2
     host = t.infer_crops_host(torch.from_numpy(crops).pin_memory())
     assert torch.equal(host, out)
+
+
+@pytest.mark.parametrize("n_frames,batch_size", [(150, 2), (40, 4)])      # 2 snippets + overlapping tail in two batches; shorter than a snippet
+def test_video_path_matches_reference_semantics(cuda, n_frames, batch_size):
+    """Tester.predict_frames / test_frames: windows clamped to the video, 64-frame snippets + tail snippet, the snippets of
+    a DataLoader batch forwarded together (GRU over the batch), tail overwrites -- api/tester.py:53-121."""
+    from tester import Tester
+    crops = _crops(n_frames, 17)
+    net = O.resnet_synthetic(1)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(), seed=1)
+    t = Tester(None, batch_size=batch_size, resnet_model=net, head_state_dict=sd)
+    got = t.predict_frames(torch.from_numpy(crops).to(cuda)).cpu()
+    assert got.shape == (n_frames, 2)
+    # the reference's procedure restated with the oracle pieces and the device entry points it is built from
+    gray = torch.from_numpy(P.crops_to_gray(crops))
+    rgb = torch.from_numpy(P.crops_to_rgb(crops))
+    ranges = O.snippet_ranges(n_frames)
+    exact, ref = [], []
+    for b0 in range(0, len(ranges), batch_size):
+        batch = ranges[b0:b0 + batch_size]
+        windows = torch.stack([O.gather_windows(gray, s, e) for s, e in batch])
+        frames_rgb = torch.cat([rgb[s:e] for s, e in batch])
+        dev = t.infer_clips(windows.to(cuda), frames_rgb.to(cuda)).cpu()
+        exact += [dev[k].numpy() for k in range(len(batch))]
+        p0, p1 = O.phase_diff_output(windows)
+        with torch.no_grad():
+            cpu = O.head_forward(sd, p0, p1, O.resnet_pool5(net, frames_rgb).view(len(batch), -1, 2048))
+        ref += [cpu[k].numpy() for k in range(len(batch))]
+    assert np.array_equal(got.numpy(), O.stitch(ranges, exact).astype(np.float32))      # same kernels, same bits
+    err = np.abs(got.numpy() - O.stitch(ranges, ref)).max()
+    print("video path (%d frames, %d snippets): valence/arousal max|err| %.3e" % (n_frames, len(ranges), err))
+    assert err < 3e-2
+    frame = t.test_frames(crops, "clip_a")
+    assert list(frame) == ["clip_a"] and list(frame["clip_a"].columns) == ["valence", "arousal"]
+    assert np.array_equal(frame["clip_a"].to_numpy().astype(np.float32), got.numpy())
+    from multi_gpu import run_videos                       # world size 1: the local block is everything
+    both = run_videos(t, [crops, crops[:n_frames - 7]])
+    assert len(both) == 2 and torch.equal(both[0].cpu(), got) and both[1].shape == (n_frames - 7, 2)
