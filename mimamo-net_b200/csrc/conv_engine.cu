@@ -1,18 +1,23 @@
 // tcgen05 implicit-GEMM convolution engine for sm_100a.
 //
-// One persistent, warp-specialised kernel serves every convolution on the hot path
-// (ResNet50's 1x1 / 3x3 / strided layers, api/resnet50_extractor.py:81, and PhaseNet's 3x3
-// layers, api/mimamo_net.py:68-90):
+// Persistent, warp-specialised kernels serve every convolution on the hot path (ResNet50's 1x1 / 3x3 /
+// strided layers, api/resnet50_extractor.py:81, and PhaseNet's 3x3 layers, api/mimamo_net.py:68-90):
 //
-//   warp 0      TMA producer: per K-block one activation box + one weight box into a ring of
-//               128B-swizzled shared-memory stages (mbarrier full/empty pipeline).  A 3x3 tap
-//               is just a shifted 4-D box over the NHWC activation tensor; TMA's out-of-bounds
-//               zero fill IS the convolution padding, and its element strides implement
-//               stride-2 layers, so no im2col buffer exists for any 1x1 / 3x3 layer.
-//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, fp32
-//               accumulators in TMEM, double buffered so tile i+1 overlaps tile i's epilogue).
-//   warps 2-5   epilogue: tcgen05.ld TMEM -> registers, folded-BatchNorm scale/shift,
-//               optional residual add + ReLU, 16-bit NHWC store.
+//   conv_gemm_kernel     1x1 layers (flat rows) and box-per-tap 3x3 / strided layers; optional "pair" mode: 2-CTA
+//                        clusters whose weight boxes are fetched half each and TMA-multicast into both CTAs
+//   conv_gemm2_kernel    the same GEMM with tcgen05.mma.cta_group::2: a CTA pair computes a 256 x 256 tile, each CTA
+//                        staging its 128 activation rows and half of the weight rows (K-heavy 256-wide layers)
+//   conv3x3_halo_kernel  stride-1 3x3 with Cout <= 128: the input patch is loaded once, nine shifted UMMA views
+//   conv1_line_kernel    conv1_7x7_s2 over the space-to-depth'ed input, pool1_3x3_s2 fused into the epilogue
+//
+//   warp 0      TMA producer: activation + weight boxes into a ring of 128B-swizzled shared-memory stages
+//               (mbarrier full/empty pipeline).  A 3x3 tap is just a shifted 4-D box over the NHWC activation
+//               tensor; TMA's out-of-bounds zero fill IS the convolution padding, and its element strides
+//               implement stride-2 layers, so no im2col buffer exists for any layer.
+//   warp 1      single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, fp32 accumulators in TMEM,
+//               double buffered so tile i+1 overlaps tile i's epilogue).
+//   warps 2-17  epilogue: tcgen05.ld TMEM -> registers (thread = output row), folded-BatchNorm scale/shift,
+//               optional residual add + ReLU, 16-bit pack, swizzled staging tile, TMA bulk-tensor store.
 //
 // D[M = output pixels][N = Cout] = A[M][K] * B[N][K]^T,  K = taps * Cin_p (K-major, 16-bit).
 #include "common.cuh"
