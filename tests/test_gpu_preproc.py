@@ -91,7 +91,8 @@ def test_infer_crops_matches_clip_path_and_oracle(cuda):
     assert torch.equal(host, out)
 
 
-@pytest.mark.parametrize("n_frames,batch_size", [(150, 2), (40, 4)])      # 2 snippets + overlapping tail in two batches; shorter than a snippet
+# 2 snippets + overlapping tail in two batches; shorter than a snippet; shorter than one 13-frame window; a single frame
+@pytest.mark.parametrize("n_frames,batch_size", [(150, 2), (40, 4), (9, 4), (1, 1)])
 def test_video_path_matches_reference_semantics(cuda, n_frames, batch_size):
     """Tester.predict_frames / test_frames: windows clamped to the video, 64-frame snippets + tail snippet, the snippets of
     a DataLoader batch forwarded together (GRU over the batch), tail overwrites -- api/tester.py:53-121."""
@@ -125,5 +126,8 @@ def test_video_path_matches_reference_semantics(cuda, n_frames, batch_size):
     assert list(frame) == ["clip_a"] and list(frame["clip_a"].columns) == ["valence", "arousal"]
     assert np.array_equal(frame["clip_a"].to_numpy().astype(np.float32), got.numpy())
     from multi_gpu import run_videos                       # world size 1: the local block is everything
-    both = run_videos(t, [crops, crops[:n_frames - 7]])
-    assert len(both) == 2 and torch.equal(both[0].cpu(), got) and both[1].shape == (n_frames - 7, 2)
+    n2 = max(1, n_frames - 7)
+    both = run_videos(t, [crops, crops[:n2]])
+    assert len(both) == 2 and torch.equal(both[0].cpu(), got) and both[1].shape == (n2, 2)
+    with pytest.raises(ValueError):
+        t.predict_frames(torch.zeros(0, 112, 112, 3, dtype=torch.uint8, device=cuda))
