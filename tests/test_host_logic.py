@@ -2,6 +2,7 @@
 keys, C-ABI exports).  No GPU compute is called here."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -94,6 +95,29 @@ def test_extractor_argument_errors_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             pde.build_pyramid(torch.zeros(1, 2, 48, 48))
+
+
+def test_crop_path_has_no_cpu_fallback():
+    """The uint8 face-crop entry points must fail loudly without a GPU (no host re-implementation hides behind them)."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from utils.crop_preprocessor import Crop_Preprocessor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Crop_Preprocessor()
+    from resnet50_extractor import Resnet50_Extractor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Resnet50_Extractor(model={})
+
+
+def test_bench_inputs_are_the_baseline_config():
+    """bench.py's workload is BASELINE.json configs[1]: 32 clips x 64 frames of 112x112x3 uint8 per GPU."""
+    sys.path.insert(0, os.path.dirname(mimamo_b200.PACKAGE_DIR))
+    import bench
+    from bench_inputs import make_crops
+    assert (bench.CLIPS, bench.FRAMES, bench.WINDOWS) == (32, 64, 2048)
+    crops = make_crops(seed=1, clips=2, frames=3)
+    assert crops.shape == (2, 3, 112, 112, 3) and crops.dtype == torch.uint8
+    assert torch.equal(crops, make_crops(seed=1, clips=2, frames=3))      # seeded: every run sees the same bits
 
 
 def test_c_abi_exports_every_declared_symbol():
