@@ -66,13 +66,20 @@ class Tester(object):
         self._window_index = {}
 
     # ------------------------------------------------------------------ reference surface
-    def test(self, input_video):
+    def test(self, input_video, fast=True):
+        """Reference entry point (api/tester.py:53-74): OpenFace -> per-frame features -> snippets -> predictions.
+        fast=True (default) decodes the aligned crops once and runs `test_frames` -- same windows, snippets, batches and
+        stitching, every transform on the device; it does not leave the reference's `<video>_pool5/%05d.npy` feature
+        cache behind.  fast=False follows the reference's file-by-file route (Resnet50_Extractor.run -> .npy ->
+        Snippet_Sampler -> DataLoader) on the same kernels."""
         from sampler.snippet_sampler import Snippet_Sampler
         if self.video_processor is None:
-            raise RuntimeError('this Tester was built from in-memory weights without OpenFace; use infer_clips')
+            raise RuntimeError('this Tester was built from in-memory weights without OpenFace; use test_frames / infer_crops')
         video_name = os.path.basename(input_video).split('.')[0]
         opface_output_dir = os.path.join(os.path.dirname(input_video), video_name + "_opface")
         self.video_processor.process(input_video, opface_output_dir)
+        if fast:
+            return self.test_frames(load_aligned_crops(opface_output_dir, video_name), video_name)
         feature_dir = os.path.join(os.path.dirname(input_video), video_name + "_pool5")
         self.resnet50_extractor.run(opface_output_dir, feature_dir, video_name=video_name)
         dataset = Snippet_Sampler(video_name, opface_output_dir, feature_dir, annot_dir=None,
@@ -298,6 +305,21 @@ class Tester(object):
         frames = torch.as_tensor(frames)
         pred = self.predict_frames(frames.to(get_device(), non_blocking=True))
         return {video_name: pd.DataFrame(data=pred.cpu().numpy().astype(np.float64), columns=self.label_name)}
+
+
+def load_aligned_crops(opface_output_dir, video_name):
+    """Decoded face crops of an OpenFace output directory, uint8 (n, S, S, 3) RGB in OpenFace frame order
+    (<dir>/<video>_aligned/frame_det_00_%06d.bmp; the order Image_Sampler / Snippet_Sampler use:
+    api/sampler/image_sampler.py:104-107, snippet_sampler.py:100-103).  Host I/O only."""
+    import glob
+    from PIL import Image
+    paths = glob.glob(os.path.join(opface_output_dir, video_name + "_aligned", '*.bmp'))
+    paths = sorted(paths, key=lambda x: os.path.basename(x).split(".")[0].split("_")[-1])
+    if len(paths) == 0:
+        raise ValueError("number of frames of video {} should not be zero.".format(video_name))
+    frames = np.stack([np.asarray(Image.open(p).convert('RGB'), dtype=np.uint8) for p in paths])
+    out = torch.from_numpy(frames)
+    return out.pin_memory() if torch.cuda.is_available() else out
 
 
 def stitch_predictions(names, ranges, preds):

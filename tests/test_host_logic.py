@@ -97,6 +97,23 @@ def test_extractor_argument_errors_without_gpu():
             pde.build_pyramid(torch.zeros(1, 2, 48, 48))
 
 
+def test_load_aligned_crops_order_and_layout(tmp_path):
+    """Tester.test's fast route decodes <video>_aligned/frame_det_00_%06d.bmp in OpenFace frame order (host I/O only)."""
+    Image = pytest.importorskip("PIL.Image")
+    from tester import load_aligned_crops
+    d = tmp_path / "clip_opface" / "clip_aligned"
+    d.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (12, 16, 16, 3), dtype=np.uint8)
+    for i in (11, 3, 0, 7, 1, 2, 10, 4, 5, 9, 6, 8):                     # written out of order
+        Image.fromarray(frames[i], "RGB").save(str(d / ("frame_det_00_%06d.bmp" % (i + 1))))
+    got = load_aligned_crops(str(tmp_path / "clip_opface"), "clip")
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (12, 16, 16, 3)
+    assert np.array_equal(got.numpy(), frames)
+    with pytest.raises(ValueError):
+        load_aligned_crops(str(tmp_path / "clip_opface"), "other")
+
+
 def test_crop_path_has_no_cpu_fallback():
     """The uint8 face-crop entry points must fail loudly without a GPU (no host re-implementation hides behind them)."""
     if torch.cuda.is_available():
