@@ -276,11 +276,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "f16", "data": "synthetic",
         "config": {"workload": "configs[1]: full MIMAMO inference (SCFpyr+phase, ResNet50 pool5, 2-stream GRU) on "
                                "32 synthetic 64-frame 112x112 clips per GPU = 2048 face-windows/step/GPU",
                    "inputs": "uint8 face crops (32,64,112,112,3) per GPU; PIL-exact preprocessing on the device",
-                   "dtypes": "preprocessing u8/int32, pyramid+phase f32, ResNet50 bf16 (f32 accumulate), PhaseNet f16, dense+GRU f32",
+                   "dtypes": "preprocessing u8/int32, pyramid+phase f32, ResNet50 f16 (f32 accumulate), PhaseNet f16, dense+GRU f32",
                    "l2": "a 256 MB buffer is rewritten before every timed step (L2 flush)", "videos_sharded_by": "rank"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": world * crops_h.numel(),

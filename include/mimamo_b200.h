@@ -78,6 +78,37 @@ int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Full pyramid of arbitrary (un-mirrored) square images and its inverse.
+ * Replaces SCFpyr_PyTorch.build / _build_levels (api/steerable/SCFpyr_PyTorch.py:70-208) -- hi0 residual, every
+ * oriented band at full size, low residual -- and SCFpyr_PyTorch.reconstruct / _reconstruct_levels (:214-314).
+ * Not on the inference hot path (that is mimamo_pyr_build above).  A plan is a list of output "units" in the order
+ * of the reference's coeff list [hi0, level 1, ..., level L, lo]; the host supplies, per unit, its size s, the gather
+ * index of its natural-order frequencies into the image's natural-order spectrum (all of the reference's
+ * fftshift / centre-crop / ifftshift steps composed) and its cumulative real masks
+ * (mimamo-net_b200/api/steerable/plan_tables.py::full_pyramid_tables).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct mimamo_scf_plan mimamo_scf_plan;
+typedef struct {
+  int32_t s;                      /* unit size (s x s)                                              */
+  int32_t planes;                 /* 1 for hi0 / lo, nbands for a level                             */
+  int32_t is_real;                /* 1: the reference keeps the real part (hi0, lo)                 */
+  int32_t twist_build;            /* multiply by (-i)^twist when building (SCFpyr_PyTorch.py:64)    */
+  int32_t twist_recon;            /* ... when reconstructing (:65)                                  */
+  const int32_t* src_index_host;  /* [s]                                                            */
+  const float*   build_mask_host; /* [planes][s][s], natural frequency order                        */
+  const float*   recon_mask_host; /* [planes][s][s]                                                 */
+} mimamo_scf_unit_desc;
+int  mimamo_scf_plan_create(int32_t S, int32_t n_units, const mimamo_scf_unit_desc* units, mimamo_scf_plan** plan_out);
+void mimamo_scf_plan_destroy(mimamo_scf_plan* plan);
+int  mimamo_scf_workspace_bytes(const mimamo_scf_plan* plan, int64_t N, size_t* bytes_out);
+/* images f32[N,S,S] -> unit_out[u]: f32[N,s,s] (real units) or f32[planes,N,s,s,2] (levels) */
+int  mimamo_scf_build(const mimamo_scf_plan* plan, const float* images, int64_t N, float* const* unit_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* the inverse: unit_in as produced by mimamo_scf_build -> images_out f32[N,S,S] */
+int  mimamo_scf_reconstruct(const mimamo_scf_plan* plan, const float* const* unit_in, int64_t N, float* images_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * P2: phase tail.  Replaces Phase_Difference_Extractor.extract
  * (api/phase_difference_extractor.py:93-134) with torch_unwrap / torch_diff /
  * amplitude_based_gaussian_blur / gaussian_kernel (api/utils/phase_utils.py:5-40,78-90,108-115).
@@ -159,6 +190,14 @@ void mimamo_resnet50_destroy(mimamo_resnet50* net);
 int  mimamo_resnet50_workspace_bytes(const mimamo_resnet50* net, int32_t batch, size_t* bytes_out);
 int  mimamo_resnet50_pool5(const mimamo_resnet50* net, const float* x, int32_t batch, float* out,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weight rounding.  The 16-bit weights are rounded so that, per output channel, the rounding residuals weighted by the
+ * mean of each input channel sum to ~0 (the error component that is identical at every pixel and therefore survives
+ * pool5's spatial average).  mimamo_resnet50_create calibrates the channel means on a built-in
+ * synthetic batch (MIMAMO_RESNET_CALIB=0/1/2: round-to-nearest / uniform means / calibrated, default 2); this call
+ * re-calibrates on the caller's images x f32[batch,3,224,224] (batch <= one pass).  No reference counterpart. */
+int  mimamo_resnet50_calibrate(mimamo_resnet50* net, const float* x, int32_t batch,
+                               void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same, from uint8 face crops [B, src, src, 3]: the RGB transform above runs on the device and
  * feeds conv1 directly (workspace as mimamo_resnet50_workspace_bytes). */

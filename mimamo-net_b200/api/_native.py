@@ -25,6 +25,12 @@ class PyrLevelDesc(ctypes.Structure):
                 ("trig_host", c_float_p), ("masks_host", c_float_p), ("inner_sel_host", c_int32_p)]
 
 
+class ScfUnitDesc(ctypes.Structure):
+    _fields_ = [("s", ctypes.c_int32), ("planes", ctypes.c_int32), ("is_real", ctypes.c_int32),
+                ("twist_build", ctypes.c_int32), ("twist_recon", ctypes.c_int32),
+                ("src_index_host", c_int32_p), ("build_mask_host", c_float_p), ("recon_mask_host", c_float_p)]
+
+
 class TensorDesc(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char_p), ("data_host", c_float_p), ("ndim", ctypes.c_int32),
                 ("shape", ctypes.c_int64 * 4)]
@@ -42,6 +48,11 @@ _SIGNATURES = {
                                                         ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_pyr_build": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(vp), vp,
                                         ctypes.c_size_t, vp]),
+    "mimamo_scf_plan_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ScfUnitDesc), ctypes.POINTER(vp)]),
+    "mimamo_scf_plan_destroy": (None, [vp]),
+    "mimamo_scf_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_size_t)]),
+    "mimamo_scf_build": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.POINTER(vp), vp, ctypes.c_size_t, vp]),
+    "mimamo_scf_reconstruct": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.c_int64, vp, vp, ctypes.c_size_t, vp]),
     "mimamo_phase_extract_workspace_bytes": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                             ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_phase_extract": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
@@ -66,6 +77,7 @@ _SIGNATURES = {
     "mimamo_resnet50_destroy": (None, [vp]),
     "mimamo_resnet50_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_resnet50_pool5": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),
+    "mimamo_resnet50_calibrate": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, ctypes.c_size_t, vp]),
     "mimamo_head_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.c_int32,
                                           ctypes.POINTER(vp)]),
     "mimamo_head_destroy": (None, [vp]),

@@ -26,6 +26,9 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <math.h>
+#include <thread>
 #include <vector>
 
 namespace mimamo {
@@ -1510,6 +1513,89 @@ static int halo_setting() {
   return e ? atoi(e) : 1;
 }
 
+// ---- 16-bit rounding of the weights ----
+static inline float f16_bits_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu;
+  uint32_t bits;
+  if (exp == 0) {
+    if (man == 0) bits = sign;
+    else { float f = ldexpf((float)man, -24); memcpy(&bits, &f, 4); bits |= sign; }
+  } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+  else bits = sign | ((exp + 112u) << 23) | (man << 13);
+  float f; memcpy(&f, &bits, 4); return f;
+}
+static inline float w16_to_float(uint16_t b, ElemType elem) {
+  if (elem == kBF16) { const uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+  return f16_bits_to_float(b);
+}
+static inline uint16_t float_to_w16(float v, ElemType elem) {
+  uint16_t bits;
+  if (elem == kBF16) { __nv_bfloat16 h = __float2bfloat16(v); memcpy(&bits, &h, 2); }
+  else { __half h = __float2half(v); memcpy(&bits, &h, 2); }
+  return bits;
+}
+// the representable neighbour of a finite 16-bit value towards -inf (down) or +inf
+static inline uint16_t w16_neighbor(uint16_t b, bool down) {
+  const bool neg = (b & 0x8000u) != 0;
+  if ((b & 0x7FFFu) == 0) return down ? 0x8001u : 0x0001u;
+  return (uint16_t)((neg == down) ? b + 1 : b - 1);          // larger magnitude when moving away from zero
+}
+
+static void quantize_rows(const float* w, uint16_t* out, int row0, int row1, size_t K, int cin_p, ElemType elem, int mode, const float* mu) {
+  std::vector<uint16_t> alt(K);
+  std::vector<double> delta(K);
+  std::vector<float> cost(K);
+  std::vector<int> order;
+  for (int o = row0; o < row1; ++o) {
+    const float* wr = w + (size_t)o * K;
+    uint16_t* q = out + (size_t)o * K;
+    double tot = 0.0;
+    order.clear();
+    for (size_t k = 0; k < K; ++k) {
+      q[k] = float_to_w16(wr[k], elem);
+      if (mode == 0 || wr[k] == 0.f) continue;               // zero weights (channel padding) stay zero
+      const double m = mu ? (double)mu[k % cin_p] : 1.0;
+      const double r = (double)w16_to_float(q[k], elem) - (double)wr[k];
+      tot += r * m;
+      if (r == 0.0 || m == 0.0) continue;
+      alt[k] = w16_neighbor(q[k], r > 0.0);
+      const float av = w16_to_float(alt[k], elem);
+      if (!(fabsf(av) < 6.0e4f)) continue;
+      const double ar = (double)av - (double)wr[k];
+      delta[k] = (ar - r) * m;
+      cost[k] = (float)(fabs(ar) - fabs(r));
+      order.push_back((int)k);
+    }
+    if (mode == 0) continue;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] < cost[b] || (cost[a] == cost[b] && a < b); });
+    for (int k : order) {                                      // cheapest flips first; take those that shrink the weighted residual sum
+      if (fabs(tot + delta[k]) < fabs(tot)) { tot += delta[k]; q[k] = alt[k]; }
+    }
+  }
+}
+
+int conv_layer_quantize(ConvLayer& L, int mode, const float* mu) {
+  const size_t K = (size_t)L.ksize * L.ksize * L.Cin_p;
+  MM_REQUIRE(L.w_f32.size() == (size_t)L.Cout * K, MIMAMO_E_VALUE, "conv_layer_quantize: layer holds no fp32 weights");
+  std::vector<uint16_t> packed((size_t)L.Cout * K);
+  unsigned nthr = std::thread::hardware_concurrency();
+  if (nthr < 1) nthr = 1;
+  if (nthr > 32) nthr = 32;
+  if (mode == 0 || (size_t)L.Cout * K < (1u << 16)) nthr = 1;
+  std::vector<std::thread> pool;
+  const int per = (L.Cout + (int)nthr - 1) / (int)nthr;
+  for (unsigned t = 0; t < nthr; ++t) {
+    const int r0 = (int)t * per, r1 = r0 + per < L.Cout ? r0 + per : L.Cout;
+    if (r0 >= r1) break;
+    if (nthr == 1) quantize_rows(L.w_f32.data(), packed.data(), r0, r1, K, L.Cin_p, L.elem, mode, mu);
+    else pool.emplace_back(quantize_rows, L.w_f32.data(), packed.data(), r0, r1, K, L.Cin_p, L.elem, mode, mu);
+  }
+  for (auto& th : pool) th.join();
+  if (!L.w_dev) MM_CUDA(cudaMalloc(&L.w_dev, packed.size() * 2));
+  MM_CUDA(cudaMemcpy(L.w_dev, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+  return MIMAMO_OK;
+}
+
 int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, const float* shift_host, int Cout,
                     int Cin, int ksize, int stride, int pad, int relu, ElemType elem) {
   MM_REQUIRE(Cout % 64 == 0, MIMAMO_E_RUNTIME, "Cout=%d must be a multiple of 64 for the tcgen05 engine", Cout);
@@ -1518,19 +1604,14 @@ int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, 
   L.block_n = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   const int taps = ksize * ksize;
   const size_t K = (size_t)taps * L.Cin_p;
-  std::vector<uint16_t> packed((size_t)Cout * K, 0);
+  L.w_f32.assign((size_t)Cout * K, 0.f);
   for (int o = 0; o < Cout; ++o)
     for (int c = 0; c < Cin; ++c)
-      for (int t = 0; t < taps; ++t) {
-        const float v = w_host[((size_t)o * Cin + c) * taps + t];
-        uint16_t bits;
-        if (elem == kBF16) { __nv_bfloat16 h = __float2bfloat16(v); memcpy(&bits, &h, 2); }
-        else { __half h = __float2half(v); memcpy(&bits, &h, 2); }
-        packed[(size_t)o * K + (size_t)t * L.Cin_p + c] = bits;
-      }
-  MM_CUDA(cudaMalloc(&L.w_dev, packed.size() * 2));
-  MM_CUDA(cudaMemcpy(L.w_dev, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
-  int rc = upload(&L.scale_dev, scale_host, (size_t)Cout);
+      for (int t = 0; t < taps; ++t)
+        L.w_f32[(size_t)o * K + (size_t)t * L.Cin_p + c] = w_host[((size_t)o * Cin + c) * taps + t];
+  int rc = conv_layer_quantize(L, 0, nullptr);
+  if (rc) return rc;
+  rc = upload(&L.scale_dev, scale_host, (size_t)Cout);
   if (rc) return rc;
   return upload(&L.shift_dev, shift_host, (size_t)Cout);
 }
@@ -1538,6 +1619,7 @@ int conv_layer_init(ConvLayer& L, const float* w_host, const float* scale_host, 
 void conv_layer_free(ConvLayer& L) {
   cudaFree(L.w_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev);
   L.w_dev = nullptr; L.scale_dev = L.shift_dev = nullptr;
+  std::vector<float>().swap(L.w_f32);
 }
 
 // Pair mode (2-CTA clusters, multicast weight boxes) pays where the weight tile dominates the bytes a tile pulls

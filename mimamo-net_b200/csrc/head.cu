@@ -35,6 +35,16 @@ static int make_phase_conv(const TensorTable& T, const std::string& conv, const 
   return conv_layer_init(L, w, sc.data(), sh.data(), cout, cin, 3, stride, 1, 1, kHeadElem);
 }
 
+// Weight rounding (conv_engine.cuh, conv_layer_quantize): PhaseNet's convolutions past the first read post-ReLU
+// activations, so their rounding residuals are steered to sum to zero over those input channels; the phase-difference
+// inputs themselves (conv_net[0][0], and the level-1 channels of the skip concat) are zero-mean by construction
+// (api/phase_difference_extractor.py:127-131) and stay round-to-nearest.  MIMAMO_HEAD_CALIB=0 disables.
+static int compensate_phase_conv(ConvLayer& L, int relu_channels) {
+  std::vector<float> mu((size_t)L.Cin_p, 0.f);
+  for (int c = 0; c < relu_channels && c < L.Cin_p; ++c) mu[c] = 1.f;
+  return conv_layer_quantize(L, 1, mu.data());
+}
+
 // Linear -> BN -> ReLU (bn_first) or Linear -> ReLU -> BN, or plain Linear (+BN)
 static int make_linear(const TensorTable& T, const std::string& lin, const std::string& bn, int out_f, int in_f, int relu,
                        bool bn_first, LinearLayer& L) {
@@ -76,6 +86,13 @@ extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_t
     const std::string pre(p);
     rc = make_phase_conv(T, pre + "0", pre + "1", chans[b][1], chans[b][0], 1, h->conv[2 * b]);
     if (!rc) rc = make_phase_conv(T, pre + "3", pre + "4", chans[b][1], chans[b][1], 2, h->conv[2 * b + 1]);
+  }
+  {
+    const char* e = getenv("MIMAMO_HEAD_CALIB");
+    if (!(e && e[0] == '0')) {
+      const int relu_in[6] = {0, 64, 64, 128, 128, 256};     // post-ReLU input channels of conv_net.{0,1,2}.{0,3}
+      for (int i = 1; i < 6 && !rc; ++i) rc = compensate_phase_conv(h->conv[i], relu_in[i]);
+    }
   }
   if (!rc) rc = make_linear(T, "phasenet.fc.0", "phasenet.fc.2", 256, 256, 1, false, h->fc0);
   if (!rc) rc = make_linear(T, "phasenet.fc.4", "phasenet.fc.6", 256, 256, 1, false, h->fc4);

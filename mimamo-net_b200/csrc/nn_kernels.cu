@@ -248,6 +248,41 @@ int avgpool_to_f32(const void* x, int N, int HW, int C, float* out, int ldo, int
   return MIMAMO_OK;
 }
 
+// ---- per-channel mean of an NHWC 16-bit tensor (weight-rounding calibration, conv_layer_quantize) ----
+// Deterministic: block b sums a fixed slice of rows per channel, a second kernel adds the slices in order.
+template <bool BF16>
+__global__ void channel_sum_kernel(const uint16_t* __restrict__ x, long long M, int C, int ld, int rows_per_block, double* __restrict__ partial) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double acc = 0.0;
+    for (long long r = r0; r < r1; ++r) acc += (double)from16<BF16>(__ldg(x + r * ld + c));
+    partial[(size_t)blockIdx.x * C + c] = acc;
+  }
+}
+__global__ void channel_mean_finish_kernel(const double* __restrict__ partial, int blocks, int C, long long M, float* __restrict__ mean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int b = 0; b < blocks; ++b) acc += partial[(size_t)b * C + c];
+  mean[c] = (float)(acc / (double)M);
+}
+
+int channel_means(const void* x, long long M, int C, int ld, float* mean_dev, double* scratch, size_t scratch_doubles, ElemType elem, cudaStream_t s) {
+  if (M == 0 || C == 0) return MIMAMO_OK;
+  int blocks = (int)(scratch_doubles / (size_t)C);
+  if (blocks > 1024) blocks = 1024;
+  MM_REQUIRE(blocks >= 1, MIMAMO_E_VALUE, "channel_means: scratch too small");
+  const int rows_per_block = (int)((M + blocks - 1) / blocks);
+  blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+  if (elem == kBF16) channel_sum_kernel<true><<<blocks, 256, 0, s>>>((const uint16_t*)x, M, C, ld, rows_per_block, scratch);
+  else channel_sum_kernel<false><<<blocks, 256, 0, s>>>((const uint16_t*)x, M, C, ld, rows_per_block, scratch);
+  MM_LAUNCH_OK();
+  channel_mean_finish_kernel<<<(C + 255) / 256, 256, 0, s>>>(scratch, blocks, C, M, mean_dev);
+  MM_LAUNCH_OK();
+  return MIMAMO_OK;
+}
+
 // ---- fp32 linear layer (head MLP / FC / GRU input projections; ~1.4 MMAC per window) ---------
 constexpr int kLinTile = 64, kLinK = 16;
 

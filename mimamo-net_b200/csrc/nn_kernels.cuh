@@ -24,6 +24,10 @@ int maxpool3x3s2_ceil(const void* x, int B, int H, int W, int C, void* out, Elem
 // mean over HW positions of NHWC 16-bit -> fp32 [N][ldo] at column offset
 int avgpool_to_f32(const void* x, int N, int HW, int C, float* out, int ldo, int relu, ElemType elem, cudaStream_t s);
 
+// per-channel mean over the M rows of an NHWC 16-bit tensor [M][ld] -> mean_dev f32[C]; deterministic (fixed-order two-stage sum);
+// scratch: at least C doubles per block (up to 1024 blocks are used)
+int channel_means(const void* x, long long M, int C, int ld, float* mean_dev, double* scratch, size_t scratch_doubles, ElemType elem, cudaStream_t s);
+
 // out[m][n] = post(relu?(pre(sum_k a[m][k] w[n][k] + bias[n])))  with per-column affine pre/post
 struct LinearLayer {
   int in_f = 0, out_f = 0, relu = 0;

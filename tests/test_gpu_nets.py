@@ -16,8 +16,9 @@ def _rgb(n, seed):
     return torch.randint(0, 256, (n, 3, 224, 224), generator=g).float() - torch.tensor(O.RESNET_MEAN)[None, :, None, None]
 
 
-@pytest.mark.parametrize("dtype,rel_tol,conv1", [("bf16", 4e-2, "line"), ("fp16", 6e-3, "line"), ("bf16", 4e-2, "im2col"),
-                                                 ("bf16", 4e-2, "line_unfused_pool")])
+# relative tolerances = 2x the error measured on B200 (fp16 5.3e-4, bf16 3.6e-3 of the feature scale); fp16 is the default
+@pytest.mark.parametrize("dtype,rel_tol,conv1", [("fp16", 6e-4, "line"), ("bf16", 7.5e-3, "line"), ("fp16", 6e-4, "im2col"),
+                                                 ("fp16", 6e-4, "line_unfused_pool")])
 def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     """Row R: parity against the restated architecture with seeded synthetic weights (parity with
     the published checkpoint is unpinned: the third-party definition/weights are absent).
@@ -37,11 +38,32 @@ def test_resnet50_pool5(cuda, dtype, rel_tol, conv1, monkeypatch):
     err = (got - ref).abs()
     print("resnet50 %s: max|err| %.3e (%.2e of scale %.3f), mean rel %.2e" % (dtype, err.max().item(), err.max().item() / scale, scale, (err.mean() / ref.abs().mean()).item()))
     assert err.max().item() < rel_tol * scale
+    assert torch.isfinite(got).all()                        # fp16 activations: nothing overflowed with 0-255-scale inputs
     vec = ext.get_vec(x[:1].to(cuda))                       # reference quirk: bs == 1 squeezes to (2048,)
     assert vec.shape == (2048,) and vec.device.type == "cpu"
     # batch composition must not matter (chunking / tile boundaries)
     again = ext.features(x[1:4].to(cuda)).cpu()
     assert torch.equal(again, got[1:4])
+
+
+def test_weight_rounding_calibration(cuda, monkeypatch):
+    """conv_layer_quantize: mean-compensated weight rounding vs plain round-to-nearest (MIMAMO_RESNET_CALIB 2 / 1 / 0),
+    same fp16 kernels.  The compensated rounding removes the error component that survives pool5's spatial average."""
+    from resnet50_extractor import Resnet50_Extractor
+    import time
+    net = O.resnet_synthetic(1)
+    x = _rgb(5, 21)
+    ref = O.resnet_pool5(net, x)
+    scale = ref.abs().max().item()
+    errs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("MIMAMO_RESNET_CALIB", mode)
+        t0 = time.time()
+        ext = Resnet50_Extractor(model=net)
+        got = ext.features(x.to(cuda)).cpu()
+        errs[mode] = (got - ref).abs().max().item() / scale
+        print("resnet50 fp16, weight rounding mode %s: max|err| %.2e of scale (create + run %.1f s)" % (mode, errs[mode], time.time() - t0))
+    assert errs["2"] < 0.6 * errs["0"] and errs["1"] < errs["0"]
 
 
 def test_fused_pool1_is_bit_identical(cuda, monkeypatch):
@@ -97,9 +119,8 @@ def test_head_batch32_recurrence(cuda):
 
 
 def test_end_to_end_clip_path(cuda):
-    """Gray windows + RGB frames -> valence/arousal through Tester.infer_clips vs the oracle chain.
-    With a 16-bit ResNet in the loop the 1e-3 budget applies to the head fed identical inputs (tests
-    above); here the whole chain is compared and the measured error is reported."""
+    """Gray windows + RGB frames -> valence/arousal through Tester.infer_clips vs the oracle chain: the whole
+    chain (pyramid + phase, fp16 ResNet50, head) inside the north_star's 1e-3 valence/arousal budget."""
     from tester import Tester
     B, Fr = 2, 8
     gen = torch.Generator().manual_seed(13)
@@ -114,7 +135,33 @@ def test_end_to_end_clip_path(cuda):
     with torch.no_grad():
         ref = O.head_forward(sd, p0, p1, O.resnet_pool5(net, rgb).view(B, Fr, 2048))
     err = (out - ref).abs().max().item()
-    print("end-to-end (bf16 ResNet): valence/arousal max|err| %.3e" % err)
-    assert out.shape == (B, Fr, 2) and err < 3e-2
+    print("end-to-end (fp16 ResNet): valence/arousal max|err| %.3e" % err)
+    assert out.shape == (B, Fr, 2) and err < VA_TOL
     host = t.infer_clips_host(gray.pin_memory(), rgb.pin_memory(), copy_chunk=5)     # ragged last chunk
     assert torch.equal(host, out)
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_end_to_end_batch32_grouping(cuda, dtype, monkeypatch):
+    """BASELINE configs[1] grouping: ONE forward over B = 32 snippets (GRU sequence length 32, api/tester.py:84-93), whole
+    chain vs the oracle.  Frames are independent GRU batch rows, so 8 frames per snippet keep the CPU oracle's ResNet50
+    affordable without changing the recurrence.  fp16 (the default) must meet the 1e-3 budget; bf16 is measured and
+    reported (it does not: that is why it is not the default)."""
+    from tester import Tester
+    monkeypatch.setenv("MIMAMO_RESNET_DTYPE", dtype)
+    B, Fr = 32, 8
+    gen = torch.Generator().manual_seed(29)
+    clip = torch.rand(B, Fr + 12, 48, 48, generator=gen)
+    gray = torch.stack([O.gather_windows(clip[b], 6, 6 + Fr) for b in range(B)])
+    rgb = _rgb(B * Fr, 30)
+    net = O.resnet_synthetic(1)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(), seed=1)
+    t = Tester(None, batch_size=B, resnet_model=net, head_state_dict=sd)
+    out = t.infer_clips(gray.to(cuda), rgb.to(cuda)).cpu()
+    p0, p1 = O.phase_diff_output(gray)
+    with torch.no_grad():
+        ref = O.head_forward(sd, p0, p1, O.resnet_pool5(net, rgb).view(B, Fr, 2048))
+    err = (out - ref).abs()
+    print("end-to-end B=32 grouping (%s ResNet): valence/arousal max|err| %.3e, mean %.3e" % (dtype, err.max().item(), err.mean().item()))
+    assert out.shape == (B, Fr, 2)
+    assert err.max().item() < (VA_TOL if dtype == "fp16" else 3e-2)
