@@ -118,6 +118,12 @@ int mimamo_phase_extract_workspace_bytes(int64_t n_maps, int32_t T, int32_t rows
                                          size_t* bytes_out);
 int mimamo_phase_extract(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Training-side variants of the same tail, Steerable_Pyramid_Phase.extract_phase(coeff, return_phase, return_both)
+ * (Aff-wild-exps/utils.py:367-418) with insert_tensors (:419-432; it fills only the first T-1 of its 2(T-1) slots,
+ * reproduced):  mode 0 = phase differences (as above), mode 1 = return_phase -> out f32[n_maps, T, rows, cols]
+ * (denoised phase minus its spatial mean), mode 2 = return_both -> out f32[n_maps, 2(T-1), rows, cols]. */
+int mimamo_phase_extract_ex(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols, int32_t mode,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * P3: frames -> phase-difference maps without materialising coefficients in the caller.
@@ -207,7 +213,7 @@ int  mimamo_resnet50_pool5_crops(const mimamo_resnet50* net, const mimamo_prepro
 
 /* H: two-stream head.  Replaces Two_Stream_RNN.forward (api/mimamo_net.py:129-143; MLP :22-26,
  * PhaseNet :79-95; GRU built without batch_first at :119, so it recurs over dim 0 = bs).
- * phase_0 f32[bs,nf,24,48,48], phase_1 f32[bs,nf,24,24,24], rgb f32[bs,nf,2048]
+ * phase_0 f32[bs,nf,C,48,48], phase_1 f32[bs,nf,C,24,24] (C = 2*num_phase, 24 by default), rgb f32[bs,nf,2048]
  * -> out f32[bs,nf,2] = [valence, arousal]. */
 typedef struct mimamo_head mimamo_head;
 int  mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_phase,
@@ -217,6 +223,25 @@ int  mimamo_head_workspace_bytes(const mimamo_head* head, int32_t bs, int32_t nf
 int  mimamo_head_forward(const mimamo_head* head, const float* phase_0, const float* phase_1,
                          const float* rgb, int32_t bs, int32_t nf, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two streams of the head on their own: MLP.forward (api/mimamo_net.py:22-26; keys `mlp.{1,2,5,6,...}`, any depth,
+ * last width 256) and PhaseNet.forward for 48x48 inputs (:79-95; keys `conv_net.*`, `fc.*`, `classifier.*`).
+ * x f32[rows, in_features] -> out f32[rows,256];  phase_0 f32[rows,C,48,48], phase_1 f32[rows,C,24,24] ->
+ * out f32[rows,256] (feature != 0) or f32[rows,1] (feature == 0: + classifier Linear(256,1) + BatchNorm1d(1)). */
+typedef struct mimamo_mlp mimamo_mlp;
+int  mimamo_mlp_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, mimamo_mlp** mlp_out);
+void mimamo_mlp_destroy(mimamo_mlp* mlp);
+int  mimamo_mlp_in_features(const mimamo_mlp* mlp);
+int  mimamo_mlp_workspace_bytes(const mimamo_mlp* mlp, int32_t rows, size_t* bytes_out);
+int  mimamo_mlp_forward(const mimamo_mlp* mlp, const float* x, int32_t rows, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+typedef struct mimamo_phasenet mimamo_phasenet;
+int  mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_channels,
+                            mimamo_phasenet** net_out);
+void mimamo_phasenet_destroy(mimamo_phasenet* net);
+int  mimamo_phasenet_workspace_bytes(const mimamo_phasenet* net, int32_t rows, size_t* bytes_out);
+int  mimamo_phasenet_forward(const mimamo_phasenet* net, const float* phase_0, const float* phase_1, int32_t rows,
+                             int32_t feature, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-launch CUDA-event timing of the tcgen05 GEMM kernel (bench.py's roofline leg).
  * enable=1 resets and starts recording; read after synchronising the stream. */

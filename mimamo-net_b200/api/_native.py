@@ -57,6 +57,8 @@ _SIGNATURES = {
                                                             ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_phase_extract": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                             vp, vp, ctypes.c_size_t, vp]),
+    "mimamo_phase_extract_ex": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                               vp, vp, ctypes.c_size_t, vp]),
     "mimamo_pyr_phase_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32,
                                                         ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_pyr_phase": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(vp), vp,
@@ -85,6 +87,15 @@ _SIGNATURES = {
                                                    ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_head_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
                                            ctypes.c_size_t, vp]),
+    "mimamo_mlp_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.POINTER(vp)]),
+    "mimamo_mlp_destroy": (None, [vp]),
+    "mimamo_mlp_in_features": (ctypes.c_int, [vp]),
+    "mimamo_mlp_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
+    "mimamo_mlp_forward": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),
+    "mimamo_phasenet_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp)]),
+    "mimamo_phasenet_destroy": (None, [vp]),
+    "mimamo_phasenet_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
+    "mimamo_phasenet_forward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),
     "mimamo_profile_gemm": (ctypes.c_int, [ctypes.c_int32]),
     "mimamo_profile_gemm_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
                                                 ctypes.POINTER(ctypes.c_double)]),

@@ -98,11 +98,14 @@ class NativeHead(_Handle):
         table, n, keep = _tensor_table(state_dict)
         _native.check(_native.lib().mimamo_head_create(table, n, num_phase, ctypes.byref(self.handle)))
 
+        self.channels = 2 * num_phase
+
     def forward(self, phase_0, phase_1, rgb):
         bs, nf = rgb.shape[0], rgb.shape[1]
         for t in (phase_0, phase_1, rgb):
             assert t.is_cuda and t.dtype == torch.float32, 'head inputs must be float32 CUDA tensors'
-        assert tuple(phase_0.shape) == (bs, nf, 24, 48, 48) and tuple(phase_1.shape) == (bs, nf, 24, 24, 24) \
+        c = self.channels
+        assert tuple(phase_0.shape) == (bs, nf, c, 48, 48) and tuple(phase_1.shape) == (bs, nf, c, 24, 24) \
             and rgb.shape[2] == 2048, 'unexpected head input shapes'
         phase_0, phase_1, rgb = phase_0.contiguous(), phase_1.contiguous(), rgb.contiguous()
         out = torch.empty((bs, nf, 2), dtype=torch.float32, device=rgb.device)
@@ -113,4 +116,59 @@ class NativeHead(_Handle):
         _native.check(lib.mimamo_head_forward(self.handle, _native.dptr(phase_0), _native.dptr(phase_1), _native.dptr(rgb),
                                               bs, nf, _native.dptr(out), _native.dptr(ws), ws.numel(),
                                               _native.stream_ptr(rgb.device)))
+        return out
+
+
+class NativeMLP(_Handle):
+    """MLP.forward on its own (mimamo_mlp_*): state_dict keys `mlp.{1,2,5,6,...}`."""
+    _destroy = 'mimamo_mlp_destroy'
+
+    def __init__(self, state_dict):
+        super().__init__()
+        _native.require_cuda('MLP')
+        table, n, keep = _tensor_table(state_dict)
+        _native.check(_native.lib().mimamo_mlp_create(table, n, ctypes.byref(self.handle)))
+        self.in_features = _native.lib().mimamo_mlp_in_features(self.handle)
+
+    def forward(self, x):
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == self.in_features, \
+            'expected a float32 CUDA matrix with %d columns' % self.in_features
+        x = x.contiguous()
+        rows = x.shape[0]
+        out = torch.empty((rows, 256), dtype=torch.float32, device=x.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_mlp_workspace_bytes(self.handle, rows, ctypes.byref(need)))
+        ws = self.workspace(max(need.value, 8), x.device)
+        _native.check(lib.mimamo_mlp_forward(self.handle, _native.dptr(x), rows, _native.dptr(out), _native.dptr(ws),
+                                             ws.numel(), _native.stream_ptr(x.device)))
+        return out
+
+
+class NativePhaseNet(_Handle):
+    """PhaseNet.forward on its own (mimamo_phasenet_*): keys `conv_net.*`, `fc.*`, `classifier.*`."""
+    _destroy = 'mimamo_phasenet_destroy'
+
+    def __init__(self, state_dict, num_channels):
+        super().__init__()
+        _native.require_cuda('PhaseNet')
+        table, n, keep = _tensor_table(state_dict)
+        _native.check(_native.lib().mimamo_phasenet_create(table, n, num_channels, ctypes.byref(self.handle)))
+        self.channels = num_channels
+
+    def forward(self, level0, level1, feature):
+        rows = level0.shape[0]
+        for t in (level0, level1):
+            assert t.is_cuda and t.dtype == torch.float32, 'PhaseNet inputs must be float32 CUDA tensors'
+        assert tuple(level0.shape) == (rows, self.channels, 48, 48) and tuple(level1.shape) == (rows, self.channels, 24, 24), \
+            'unexpected PhaseNet input shapes'
+        level0, level1 = level0.contiguous(), level1.contiguous()
+        out = torch.empty((rows, 256 if feature else 1), dtype=torch.float32, device=level0.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_phasenet_workspace_bytes(self.handle, rows, ctypes.byref(need)))
+        ws = self.workspace(need.value, level0.device)
+        _native.check(lib.mimamo_phasenet_forward(self.handle, _native.dptr(level0), _native.dptr(level1), rows,
+                                                  1 if feature else 0, _native.dptr(out), _native.dptr(ws), ws.numel(),
+                                                  _native.stream_ptr(level0.device)))
         return out

@@ -2,7 +2,8 @@
 
 `Two_Stream_RNN` stays an `nn.Module` so `load_state_dict(checkpoint['state_dict'])`
 (api/tester.py:47-48), `.eval()` and `.to(device)` behave as before; its eval-mode forward is one
-call into libmimamo_b200.so (mimamo_head_forward).  Training is out of scope.
+call into libmimamo_b200.so (mimamo_head_forward).  `MLP` and `PhaseNet` also run on their own
+(mimamo_mlp_forward / mimamo_phasenet_forward).  Training is out of scope.
 """
 import torch
 import torch.nn as nn
@@ -23,8 +24,22 @@ class MLP(nn.Module):
             layers += _dense(i, o, dropout)
         self.mlp = nn.Sequential(*layers)
 
+        self._native = None
+
+    def load_state_dict(self, *args, **kwargs):
+        self._native = None
+        return super(MLP, self).load_state_dict(*args, **kwargs)
+
     def forward(self, input_tensor):
-        raise NotImplementedError('MLP runs inside Two_Stream_RNN.forward (mimamo_head_forward)')
+        """(bs, num_frames, features) -> (bs, num_frames, 256), eval mode (reference :22-26), via mimamo_mlp_forward.
+        Inside Two_Stream_RNN.forward the same layers run as part of mimamo_head_forward."""
+        if self.training:
+            raise RuntimeError('MLP (B200) is inference only: call .eval() first')
+        if self._native is None:
+            self._native = _nets.NativeMLP(self.state_dict())
+        bs, num_frames, feature_dim = input_tensor.size()
+        with torch.no_grad():
+            return self._native.forward(input_tensor.reshape(bs * num_frames, feature_dim)).view(bs, num_frames, -1)
 
 
 class PhaseNet(nn.Module):
@@ -33,7 +48,11 @@ class PhaseNet(nn.Module):
         if input_size not in [48, 96, 112]:
             raise ValueError("Incorrect input size")
         if input_size != 48:
-            raise NotImplementedError('only the 48x48 PhaseNet used by Two_Stream_RNN has CUDA kernels')
+            raise NotImplementedError('only the 48x48 PhaseNet used by Two_Stream_RNN has CUDA kernels '
+                                      '(the 96 / 112 variants of api/mimamo_net.py:31-38 are built by no reference caller)')
+        if list(hidden_units) != [256, 256, 1]:
+            raise NotImplementedError('the CUDA PhaseNet is built for hidden_units=[256, 256, 1]')
+        self.num_channels = num_channels
         widths = [64, 128, 256]
         ins = [num_channels, num_channels + 64, 128]
         self.conv_net = nn.ModuleList([self._block(i, o) for i, o in zip(ins, widths)])
@@ -53,17 +72,33 @@ class PhaseNet(nn.Module):
         return nn.Sequential(nn.Conv2d(i, o, 3, padding=1), nn.BatchNorm2d(o), nn.ReLU(inplace=True),
                              nn.Conv2d(o, o, 3, padding=1, stride=2), nn.BatchNorm2d(o), nn.ReLU(inplace=True))
 
+    def load_state_dict(self, *args, **kwargs):
+        self._native = None
+        return super(PhaseNet, self).load_state_dict(*args, **kwargs)
+
     def forward(self, data_level0, data_level1):
-        raise NotImplementedError('PhaseNet runs inside Two_Stream_RNN.forward (mimamo_head_forward)')
+        """(bs, frames, C, 48, 48), (bs, frames, C, 24, 24) -> (bs*frames, 256) when `feature` else (bs*frames, 1), eval
+        mode (reference :79-95), via mimamo_phasenet_forward."""
+        if self.training:
+            raise RuntimeError('PhaseNet (B200) is inference only: call .eval() first')
+        if getattr(self, '_native', None) is None:
+            self._native = _nets.NativePhaseNet(self.state_dict(), self.num_channels)
+        bs, num_frames, num_channel, W0, H0 = data_level0.size()
+        bs, num_frames, num_channel, W1, H1 = data_level1.size()
+        with torch.no_grad():
+            return self._native.forward(data_level0.reshape(bs * num_frames, num_channel, W0, H0),
+                                        data_level1.reshape(bs * num_frames, num_channel, W1, H1), self.feature)
 
 
 class Two_Stream_RNN(nn.Module):
     def __init__(self, mlp_hidden_units=[2048, 256, 256], dropout=0.5, label_name='arousal_valence',
                  num_phase=12):
         super(Two_Stream_RNN, self).__init__()
-        if list(mlp_hidden_units) != [2048, 256, 256] or len(label_name.split("_")) != 2:
-            raise NotImplementedError('the CUDA head is built for the published configuration '
-                                      '(mlp [2048,256,256], two labels)')
+        if mlp_hidden_units[0] != 2048 or len(label_name.split("_")) != 2:
+            raise NotImplementedError('the CUDA head takes 2048 ResNet50 features and predicts two labels '
+                                      '(label_name "arousal_valence"); any MLP depth / widths ending in 256 are fine')
+        if not 1 <= num_phase <= 32:
+            raise NotImplementedError('num_phase must be in [1, 32]')
         self.mlp = MLP(mlp_hidden_units)
         self.num_phase = num_phase
         self.phasenet = PhaseNet(48, 2 * num_phase, hidden_units=[256, 256, 1], dropout=0.3, feature=True)

@@ -41,9 +41,6 @@ class Phase_Difference_Extractor(object):
     def _prepare(self, im_batch, symmetry):
         bs, num_phase_frames, W, H = im_batch.size()                   # ValueError unless 4-D (:42)
         self.pyramid._check_frames(im_batch.view(bs * num_phase_frames, 1, W, H))
-        if not symmetry:
-            raise NotImplementedError('symmetry=False (no mirror extension) has no CUDA kernel; the '
-                                      'inference path always mirrors (reference :38,44-45)')
         if W != H:
             raise RuntimeError('frames must be square: the reference builds its masks with swapped '
                                'axes (SCFpyr_PyTorch.py:87,94) and cannot broadcast otherwise')
@@ -54,6 +51,8 @@ class Phase_Difference_Extractor(object):
         """im_batch (bs, T, W, H) float32 on get_device() -> coefficients (bs, nbands, T, c, c, 2)
         per requested level (a tensor for an int extract_level, a list otherwise), c = level size
         after the reference's quadrant crop (:72-75,84-85)."""
+        if not symmetry:
+            return self._build_unmirrored(im_batch)
         plan, bs, T, frames = self._prepare(im_batch, symmetry)
         outs = [torch.empty((bs, self.nbands, T, c, c, 2), dtype=torch.float32, device=frames.device)
                 for c in plan.crops]
@@ -66,6 +65,22 @@ class Phase_Difference_Extractor(object):
                                                _native.dptr(ws), ws.numel(), _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
+    def _build_unmirrored(self, im_batch):
+        """symmetry=False (reference :38-45,76-86 without the mirror extension and the quadrant crop): the frames go
+        through SCFpyr_PyTorch.build as they are and the requested levels are stacked (nb, bs*T, s, s, 2) ->
+        (bs, nb, T, s, s, 2)."""
+        bs, T, W, H = im_batch.size()
+        coeff = self.pyramid.build(im_batch.reshape(bs * T, 1, W, H))
+        if not isinstance(coeff, list):
+            raise ValueError('Batch of coefficients must be a list')
+
+        def one(level):
+            stacked = self.extract_coeff_level(level, coeff)
+            nb, _, s0, s1, _ = stacked.size()
+            return stacked.view(nb, bs, T, s0, s1, 2).permute(1, 0, 2, 3, 4, 5).contiguous()
+
+        return one(self.extract_level) if isinstance(self.extract_level, int) else [one(l) for l in self._levels()]
+
     def extract_coeff_level(self, level, coeff_batch):
         extr_level_coeff_batch = coeff_batch[level]
         assert isinstance(extr_level_coeff_batch, list)
@@ -73,20 +88,27 @@ class Phase_Difference_Extractor(object):
 
     def extract(self, coeff_batch):
         """coeff (bs, nbands, T, W, H, 2) -> phase differences (bs, nbands, T-1, W, H) (reference :93-134)."""
+        return self._tail(coeff_batch, 0)
+
+    def _tail(self, coeff_batch, mode):
+        """mimamo_phase_extract_ex: mode 0 = differences (T-1 maps), 1 = denoised phases (T), 2 = return_both layout."""
         bs, n_bands, n_phase_frames, W, H, _ = coeff_batch.size()
         _native.require_cuda('Phase_Difference_Extractor.extract')
         assert coeff_batch.is_cuda and coeff_batch.dtype == torch.float32, 'coefficients must be float32 on the GPU'
         coeff = coeff_batch.contiguous()
-        out = torch.empty((bs, n_bands, n_phase_frames - 1, W, H), dtype=torch.float32, device=coeff.device)
+        slots = (n_phase_frames - 1, n_phase_frames, 2 * (n_phase_frames - 1))[mode]
+        out = torch.empty((bs, n_bands, slots, W, H), dtype=torch.float32, device=coeff.device)
         if out.numel() == 0:
             return out
+        if n_phase_frames < 2:
+            raise ValueError('the phase tail needs at least two frames')
         lib = _native.lib()
         need = ctypes.c_size_t(0)
         _native.check(lib.mimamo_phase_extract_workspace_bytes(bs * n_bands, n_phase_frames, W, H, ctypes.byref(need)))
         ws = torch.empty((max(need.value, 8),), dtype=torch.uint8, device=coeff.device)
-        _native.check(lib.mimamo_phase_extract(_native.dptr(coeff), bs * n_bands, n_phase_frames, W, H,
-                                               _native.dptr(out), _native.dptr(ws), ws.numel(),
-                                               _native.stream_ptr(coeff.device)))
+        _native.check(lib.mimamo_phase_extract_ex(_native.dptr(coeff), bs * n_bands, n_phase_frames, W, H, mode,
+                                                  _native.dptr(out), _native.dptr(ws), ws.numel(),
+                                                  _native.stream_ptr(coeff.device)))
         return out
 
     def phase_difference(self, im_batch):
@@ -138,3 +160,37 @@ class Phase_Difference_Extractor(object):
     def show_3D_subplots(self, data, title, first_k_frames=None):
         raise NotImplementedError('visualisation is out of scope (the reference method uses undefined '
                                   'plt/cm names, api/phase_difference_extractor.py:136-152)')
+
+
+class Steerable_Pyramid_Phase(Phase_Difference_Extractor):
+    """Drop-in for the training-side copy of the extractor, `Steerable_Pyramid_Phase` (Aff-wild-exps/utils.py:298-451,
+    duplicated in OMG-exps/utils.py): same pyramid and tail, plus `extract_phase(coeff, return_phase, return_both)`
+    (:367-418) -- SURVEY.md section 8(f).4.  Constructor order as in the reference (device before extract_level)."""
+
+    def __init__(self, height=5, nbands=4, scale_factor=2, device=None, extract_level=1, visualize=False):
+        super().__init__(height=height, nbands=nbands, scale_factor=scale_factor, extract_level=extract_level,
+                         visualize=visualize)
+        if device is not None and torch.device(device) != self.pyramid.device:
+            raise RuntimeError('Steerable_Pyramid_Phase runs on {} (no CPU kernels); got device={}'.format(
+                self.pyramid.device, device))
+        self.device = self.pyramid.device
+
+    def extract_phase(self, coeff_batch, return_phase=False, return_both=False):
+        """coeff (bs, nbands, T, W, H, 2) -> phase differences (bs, nbands, T-1, W, H); return_phase: the denoised
+        phases minus their spatial mean (bs, nbands, T, W, H); return_both: insert_tensors(differences, phases[:, :, 1:])
+        (bs, nbands, 2(T-1), W, H) -- the reference's insert_tensors (:419-432) only fills the first T-1 slots."""
+        if return_both:
+            return self._tail(coeff_batch, 2)
+        return self._tail(coeff_batch, 1 if return_phase else 0)
+
+    def insert_tensors(self, t_a, t_b, dim):
+        """Reference :419-432, kept for API completeness (torch indexing, no kernel): slots i < t_a.size(dim) of a
+        tensor twice as long along `dim` alternate t_a[i // 2], t_b[i // 2]; the other half stays zero."""
+        size = list(t_a.size())
+        length = size[dim]
+        size[dim] = 2 * length
+        result = torch.zeros(size, dtype=t_a.dtype, device=t_a.device)
+        for i in range(length):
+            src = t_a if i % 2 == 0 else t_b
+            result.narrow(dim, i, 1).copy_(src.narrow(dim, i // 2, 1))
+        return result

@@ -231,3 +231,97 @@ def emulate(tables: PyramidTables, frames: np.ndarray, dtype=np.float64) -> List
                 res[:, b, :, :, ch] = acc[:, :lv.c, :lv.c]
         outs.append(res)
     return outs
+
+
+# ---- full pyramid of un-mirrored images (SCFpyr_PyTorch.build / reconstruct) ----------------------
+
+
+@dataclass
+class ScfUnit:
+    s: int                     # unit size (s x s)
+    planes: int                # 1 (hi0 / lo) or nbands (an oriented level)
+    is_real: bool              # the reference keeps only the real part (hi0, lo)
+    twist_build: int           # band spectrum times (-i)^twist (SCFpyr_PyTorch.py:64,165-168)
+    twist_recon: int           # (i)^(nb-1) = (-i)^(3 (nb-1)) when reconstructing (:65,284-287)
+    src_index: np.ndarray      # int32 [s]: natural-order frequency u of the unit -> natural-order index in the image spectrum
+    build_mask: np.ndarray     # float32 [planes][s][s], natural order, cumulative (lo0 . lomasks . himask . anglemask)
+    recon_mask: np.ndarray     # float32 [planes][s][s]
+
+
+def _natural(mask_shifted: np.ndarray) -> np.ndarray:
+    """ifftshift as the reference does it (roll by floor(n/2), api/steerable/math_utils.py:42-47)."""
+    s0, s1 = mask_shifted.shape[-2:]
+    return np.roll(mask_shifted, shift=(-(s0 // 2), -(s1 // 2)), axis=(-2, -1))
+
+
+def full_pyramid_tables(size: int, height: int, nbands: int) -> List[ScfUnit]:
+    """Units [hi0, level 1, ..., level height-2, lo] of SCFpyr_PyTorch.build for size x size images.
+
+    Every fftshift (out[i] = in[(i + ceil(n/2)) % n], math_utils.py:32-40), centre crop (SCFpyr_PyTorch.py:179-190)
+    and ifftshift of the reference is an index permutation; they are composed here into one gather index per unit,
+    and the real masks the spectrum meets on its way to a unit are multiplied up in float64."""
+    if height > max_height(size):
+        raise RuntimeError("Cannot build {} levels, image too small.".format(height))
+    if nbands < 2:
+        raise RecursionError("nbands must be >= 2 (the reference's factorial(0) never terminates, "
+                             "api/steerable/math_utils.py:79-84)")
+    log_rad, angle = _polar_grid(size, size)
+    xr, yr = _rcos()
+    lo0 = _interp(log_rad, np.sqrt(1 - yr ** 2), xr)
+    hi0 = _interp(log_rad, yr, xr)
+    lutsize = 1024
+    xcosn = np.pi * np.arange(-(2 * lutsize + 1), lutsize + 2) / lutsize
+    alpha = (xcosn + np.pi) % (2 * np.pi) - np.pi
+    order = nbands - 1
+    const = (2 ** (2 * order)) * math.factorial(order) ** 2 / (nbands * math.factorial(2 * order))
+    ycosn_build = 2 * np.sqrt(const) * np.cos(xcosn) ** order * (np.abs(alpha) < np.pi / 2)
+    ycosn_recon = np.sqrt(const) * np.cos(xcosn) ** order                    # SCFpyr_PyTorch.py:268
+    tb, tr = (nbands - 1) % 4, (3 * (nbands - 1)) % 4
+
+    def unit(idx_shifted, planes, is_real, bm, rm, twb, twr):
+        s = idx_shifted.shape[0]
+        src = np.roll(idx_shifted, -(s // 2)).astype(np.int32)               # ifftshift of the index map
+        return ScfUnit(s, planes, is_real, twb, twr, src, np.ascontiguousarray(_natural(bm), np.float32),
+                       np.ascontiguousarray(_natural(rm), np.float32))
+
+    idx = (np.arange(size) + (size + 1) // 2) % size                         # shifted position -> natural index
+    units = [unit(idx, 1, True, hi0[None], hi0[None], 0, 0)]
+    low = lo0
+    for _ in range(height - 2):
+        xr = xr - 1.0
+        hi = _interp(log_rad, yr, xr)
+        bm = np.stack([low * hi * _interp(angle, ycosn_build, xcosn + np.pi * b / nbands) for b in range(nbands)])
+        rm = np.stack([low * hi * _interp(angle, ycosn_recon, xcosn + np.pi * b / nbands) for b in range(nbands)])
+        units.append(unit(idx, nbands, False, bm, rm, tb, tr))
+        r0, r1 = _crop(log_rad.shape[0])
+        c0, c1 = _crop(log_rad.shape[1])
+        log_rad, angle = log_rad[r0:r1, c0:c1], angle[r0:r1, c0:c1]
+        idx = idx[r0:r1]
+        low = low[r0:r1, c0:c1] * _interp(log_rad, np.abs(np.sqrt(1 - yr ** 2)), xr)
+    units.append(unit(idx, 1, True, low[None], low[None], 0, 0))
+    return units
+
+
+def emulate_full(units: List[ScfUnit], images: np.ndarray):
+    """NumPy statement of mimamo_scf_build (float64): images (N,S,S) -> coeff list shaped like the reference's."""
+    F = np.fft.fft2(images.astype(np.float64))
+    out = []
+    for u in units:
+        z = F[:, u.src_index][:, :, u.src_index][None] * u.build_mask.astype(np.float64)[:, None]
+        z = z * ((-1j) ** u.twist_build)
+        c = np.fft.ifft2(z)
+        out.append(c[0].real if u.is_real else [c[b] for b in range(u.planes)])
+    return out
+
+
+def emulate_reconstruct(units: List[ScfUnit], coeff, size: int):
+    """NumPy statement of mimamo_scf_reconstruct (float64)."""
+    acc = None
+    for u, c in zip(units, coeff):
+        planes = np.stack(c) if not u.is_real else np.asarray(c)[None]
+        B = np.fft.fft2(planes.astype(np.complex128))
+        contrib = (B * u.recon_mask.astype(np.float64)[:, None]).sum(0) * ((-1j) ** u.twist_recon)
+        if acc is None:
+            acc = np.zeros((contrib.shape[0], size, size), np.complex128)
+        acc[np.ix_(np.arange(acc.shape[0]), u.src_index, u.src_index)] += contrib
+    return np.fft.ifft2(acc).real

@@ -107,10 +107,9 @@ class Tester(object):
         preds = np.concatenate(preds, axis=0)
         ranges = np.concatenate(ranges, axis=0)
         if train_mean is not None and train_std is not None:
-            # the reference calls an undefined `correct` here (api/tester.py:101); rescale each label
-            for i in range(preds.shape[-1]):
-                p = preds[..., i]
-                preds[..., i] = (p - p.mean()) / (p.std() + 1e-12) * train_std[i] + train_mean[i]
+            # the reference calls an undefined `correct(...)` here (api/tester.py:99-101) and dies with a NameError;
+            # there is no reference semantics to reproduce, so say so instead of inventing a rescaling
+            raise NotImplementedError("train_mean / train_std: the reference's `correct` is undefined (api/tester.py:101)")
         return {video: pd.DataFrame(data=arr, columns=self.label_name)
                 for video, arr in stitch_predictions(names, ranges, preds).items()}
 
@@ -296,6 +295,64 @@ class Tester(object):
                 pred = self.model([p0, p1], feats.index_select(0, rows).view(len(batch), L, -1))
                 for k, (s, e) in enumerate(batch):                        # in order: the tail snippet overwrites its overlap
                     out[s:e] = pred[k]
+        return out
+
+    def predict_videos(self, videos, group_frames=4096):
+        """Several videos at once: list of uint8 (n_v, S, S, 3) device tensors -> list of (n_v, 2) predictions, each
+        bit-identical to predict_frames(video).  The per-frame work (preprocessing, pyramid, ResNet50 -- nothing in it
+        couples frames of different videos, and the kernels are independent of the batch composition) runs over groups
+        of whole videos of about `group_frames` frames so the tensor-core passes stay full; the head then runs per
+        video, one forward per DataLoader batch of that video's snippets, exactly as `test` does
+        (api/tester.py:65-73: a batch never mixes videos)."""
+        from sampler.snippet_sampler import snippet_ranges, window_index
+        out = [None] * len(videos)
+        i = 0
+        with torch.no_grad():
+            pre = self.crop_preprocessor()
+            while i < len(videos):
+                j, total = i, 0
+                while j < len(videos) and (j == i or total + videos[j].shape[0] <= group_frames):
+                    if videos[j].shape[0] == 0:
+                        raise ValueError("number of frames of video should not be zero.")
+                    total += videos[j].shape[0]
+                    j += 1
+                group = videos[i:j]
+                device = group[0].device
+                frames = group[0] if len(group) == 1 else torch.cat(group, 0)
+                offs = [0]
+                for v in group:
+                    offs.append(offs[-1] + v.shape[0])
+                key = ('videos', tuple(v.shape[0] for v in group), str(device))
+                if key not in self._window_index:
+                    if len(self._window_index) > 64:
+                        self._window_index.clear()
+                    idx = torch.cat([window_index(0, v.shape[0], v.shape[0], self.num_phase) + o
+                                     for v, o in zip(group, offs)])
+                    self._window_index[key] = idx.to(device=device, dtype=torch.int32)
+                idx = self._window_index[key]
+                diffs = self.phase_difference_extractor.phase_difference_indexed(pre.gray(frames), idx)
+                phase = [d.view(total, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+                feats = self.resnet50_extractor.features_from_crops(frames, pre)
+                for v, o, k in zip(group, offs, range(i, j)):
+                    n = v.shape[0]
+                    ranges = snippet_ranges(n, self.length, self.stride)
+                    pred_v = torch.zeros((n, len(self.label_name)), dtype=torch.float32, device=device)
+                    for b0 in range(0, len(ranges), self.batch_size):
+                        batch = ranges[b0:b0 + self.batch_size]
+                        L = batch[0][1] - batch[0][0]
+                        whole = all(e - s == L and s == batch[0][0] + q * L for q, (s, e) in enumerate(batch))
+                        if whole:                                             # consecutive snippets: plain views, no gather
+                            lo, hi = o + batch[0][0], o + batch[-1][1]
+                            p0, p1, ft = phase[0][lo:hi], phase[1][lo:hi], feats[lo:hi]
+                        else:
+                            rows = torch.cat([torch.arange(o + s, o + e, device=device) for s, e in batch])
+                            p0, p1, ft = phase[0].index_select(0, rows), phase[1].index_select(0, rows), feats.index_select(0, rows)
+                        pred = self.model([p0.reshape(len(batch), L, *phase[0].shape[1:]),
+                                           p1.reshape(len(batch), L, *phase[1].shape[1:])], ft.reshape(len(batch), L, -1))
+                        for q, (s, e) in enumerate(batch):
+                            pred_v[s:e] = pred[q]
+                    out[k] = pred_v
+                i = j
         return out
 
     def test_frames(self, frames, video_name='video'):

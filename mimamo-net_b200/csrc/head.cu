@@ -11,16 +11,36 @@
 #include "nn_kernels.cuh"
 #include "tensor_table.cuh"
 #include <stdlib.h>
+#include <string>
 
 using namespace mimamo;
 
-struct mimamo_head {
-  int num_phase = 12, cin0 = 24;
+namespace {
+// MLP (api/mimamo_net.py:6-26): [Dropout, Linear, BN, ReLU] per hidden layer
+struct MlpPart {
+  std::vector<LinearLayer> layers;
+  int in_f = 0, max_f = 0;
+};
+// PhaseNet for 48x48 inputs (api/mimamo_net.py:27-95)
+struct PhaseNetPart {
+  int cin0 = 24;                          // phase channels = nbands * num_phase
   ConvLayer conv[6];                      // conv_net.{0,1,2}.{0,3}
-  LinearLayer mlp1, mlp2, fc0, fc4, transform, xproj[2], classifier;
+  LinearLayer fc0, fc4, cls;
+  bool has_cls = false;
+  int chunk = 1024;                       // windows per convolution pass
+};
+}  // namespace
+
+struct mimamo_mlp { MlpPart p; };
+struct mimamo_phasenet { PhaseNetPart p; };
+
+struct mimamo_head {
+  int num_phase = 12;
+  MlpPart mlp;
+  PhaseNetPart pn;
+  LinearLayer transform, xproj[2], classifier;
   float* whhT[2] = {nullptr, nullptr};    // [2 dir][128][384] per layer
   float* bhh[2] = {nullptr, nullptr};     // [2 dir][384] per layer
-  int conv_chunk = 1024;                  // windows per PhaseNet pass
 };
 
 static const ElemType kHeadElem = kF16;
@@ -47,22 +67,138 @@ static int compensate_phase_conv(ConvLayer& L, int relu_channels) {
 
 // Linear -> BN -> ReLU (bn_first) or Linear -> ReLU -> BN, or plain Linear (+BN)
 static int make_linear(const TensorTable& T, const std::string& lin, const std::string& bn, int out_f, int in_f, int relu,
-                       bool bn_first, LinearLayer& L) {
+                       bool bn_first, LinearLayer& L, float bn_eps = 1e-5f) {
   const float* w = T.get(lin + ".weight", (int64_t)out_f * in_f);
   const float* b = T.get(lin + ".bias", out_f);
   if (!w || !b) return MIMAMO_E_VALUE;
   std::vector<float> sc, sh;
-  if (!bn.empty() && !fold_bn(T, bn, out_f, 1e-5f, nullptr, sc, sh)) return MIMAMO_E_VALUE;
+  if (!bn.empty() && !fold_bn(T, bn, out_f, bn_eps, nullptr, sc, sh)) return MIMAMO_E_VALUE;
   const float* s = bn.empty() ? nullptr : sc.data();
   const float* t = bn.empty() ? nullptr : sh.data();
   return bn_first ? linear_init(L, w, b, out_f, in_f, relu, s, t, nullptr, nullptr)
                   : linear_init(L, w, b, out_f, in_f, relu, nullptr, nullptr, s, t);
 }
 
+// `pre` = key prefix of the nn.Sequential ("mlp.mlp." inside Two_Stream_RNN, "mlp." for a bare MLP); layer i owns
+// keys 4i+1 (Linear) and 4i+2 (BatchNorm1d).  Any depth / widths; the last width must be 256 (reference :12).
+static int mlp_init(const TensorTable& T, const std::string& pre, MlpPart& P) {
+  for (int i = 0;; ++i) {
+    const std::string lin = pre + std::to_string(4 * i + 1), bn = pre + std::to_string(4 * i + 2);
+    const mimamo_tensor_desc* d = T.find(lin + ".weight");
+    if (!d) break;
+    MM_REQUIRE(d->ndim == 2, MIMAMO_E_VALUE, "'%s.weight' must be 2-D", lin.c_str());
+    const int out_f = (int)d->shape[0], in_f = (int)d->shape[1];
+    MM_REQUIRE(P.layers.empty() || P.layers.back().out_f == in_f, MIMAMO_E_VALUE, "MLP layer %d does not chain", i);
+    P.layers.emplace_back();
+    int rc = make_linear(T, lin, bn, out_f, in_f, 1, true, P.layers.back());
+    if (rc) return rc;
+    if (i == 0) P.in_f = in_f;
+    P.max_f = out_f > P.max_f ? out_f : P.max_f;
+  }
+  MM_REQUIRE(!P.layers.empty(), MIMAMO_E_VALUE, "state_dict holds no '%s1.weight'", pre.c_str());
+  MM_REQUIRE(P.layers.back().out_f == 256, MIMAMO_E_RUNTIME, "the MLP must end in 256 features (api/mimamo_net.py:12)");
+  return MIMAMO_OK;
+}
+static void mlp_free(MlpPart& P) { for (auto& l : P.layers) linear_free(l); P.layers.clear(); }
+static size_t mlp_tmp_floats(const MlpPart& P, int M) { return P.layers.size() > 1 ? 2 * (size_t)M * P.max_f : 0; }
+// x [M][in_f] -> out [M][ldo] (256 columns); tmp: mlp_tmp_floats
+static int mlp_run(const MlpPart& P, const float* x, int M, float* out, int ldo, float* tmp, cudaStream_t s) {
+  const float* cur = x;
+  int ld = P.in_f;
+  for (size_t i = 0; i < P.layers.size(); ++i) {
+    const bool last = i + 1 == P.layers.size();
+    float* dst = last ? out : tmp + (i & 1) * (size_t)M * P.max_f;
+    const int ldd = last ? ldo : P.layers[i].out_f;
+    int rc = linear_forward(P.layers[i], cur, ld, M, dst, ldd, s);
+    if (rc) return rc;
+    cur = dst; ld = ldd;
+  }
+  return MIMAMO_OK;
+}
+
+static int phasenet_init(const TensorTable& T, const std::string& pre, int cin0, PhaseNetPart& P) {
+  MM_REQUIRE(cin0 >= 1 && cin0 <= 64, MIMAMO_E_RUNTIME, "PhaseNet supports 1..64 phase channels (2*num_phase), got %d", cin0);
+  P.cin0 = cin0;
+  { const char* e = getenv("MIMAMO_HEAD_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
+  const int chans[3][2] = {{cin0, 64}, {cin0 + 64, 128}, {128, 256}};
+  int rc = MIMAMO_OK;
+  for (int b = 0; b < 3 && !rc; ++b) {
+    const std::string blk = pre + "conv_net." + std::to_string(b) + ".";
+    rc = make_phase_conv(T, blk + "0", blk + "1", chans[b][1], chans[b][0], 1, P.conv[2 * b]);
+    if (!rc) rc = make_phase_conv(T, blk + "3", blk + "4", chans[b][1], chans[b][1], 2, P.conv[2 * b + 1]);
+  }
+  {
+    const char* e = getenv("MIMAMO_HEAD_CALIB");
+    if (!(e && e[0] == '0')) {
+      const int relu_in[6] = {0, 64, 64, 128, 128, 256};     // post-ReLU input channels of conv_net.{0,1,2}.{0,3}
+      for (int i = 1; i < 6 && !rc; ++i) rc = compensate_phase_conv(P.conv[i], relu_in[i]);
+    }
+  }
+  if (!rc) rc = make_linear(T, pre + "fc.0", pre + "fc.2", 256, 256, 1, false, P.fc0);
+  if (!rc) rc = make_linear(T, pre + "fc.4", pre + "fc.6", 256, 256, 1, false, P.fc4);
+  if (!rc && T.find(pre + "classifier.0.weight")) {            // Linear(256, 1) + BatchNorm1d(1, eps=1e-6) (reference :62-64)
+    rc = make_linear(T, pre + "classifier.0", pre + "classifier.1", 1, 256, 0, true, P.cls, 1e-6f);
+    P.has_cls = rc == MIMAMO_OK;
+  }
+  return rc;
+}
+static void phasenet_free(PhaseNetPart& P) {
+  for (auto& c : P.conv) conv_layer_free(c);
+  linear_free(P.fc0); linear_free(P.fc4); linear_free(P.cls);
+}
+
+namespace {
+struct PhaseNetLayout { size_t pool, fc, a0, a1, cat, a2, a3, a4, a5, total; };
+PhaseNetLayout phasenet_layout(const PhaseNetPart& P, int M) {
+  PhaseNetLayout L;
+  size_t cur = 0;
+  auto take = [&](size_t bytes) { size_t at = cur; cur += align_up(bytes, 1024); return at; };
+  const size_t Mc = (size_t)(M < P.chunk ? M : P.chunk);
+  L.pool = take((size_t)M * 256 * 4);
+  L.fc = take((size_t)M * 256 * 4);
+  L.a0 = take(Mc * 48 * 48 * 64 * 2);     // phase_0 as NHWC (cin0 -> 64 channels)
+  L.a1 = take(Mc * 48 * 48 * 64 * 2);     // conv_net[0][0]
+  L.cat = take(Mc * 24 * 24 * 128 * 2);   // [conv_net[0][3] (64) | phase_1 (cin0) | zero pad]
+  L.a2 = take(Mc * 24 * 24 * 128 * 2);    // conv_net[1][0]
+  L.a3 = take(Mc * 12 * 12 * 128 * 2);    // conv_net[1][3]
+  L.a4 = take(Mc * 12 * 12 * 256 * 2);    // conv_net[2][0]
+  L.a5 = take(Mc * 6 * 6 * 256 * 2);      // conv_net[2][3]
+  L.total = cur;
+  return L;
+}
+}  // namespace
+
+// phase_0 f32[M,cin0,48,48], phase_1 f32[M,cin0,24,24] -> out[m][0..256) at pitch ldo (the `feature=True` output)
+static int phasenet_run(const PhaseNetPart& P, const float* phase_0, const float* phase_1, int M, float* out, int ldo,
+                        char* ws, cudaStream_t s) {
+  const PhaseNetLayout L = phasenet_layout(P, M);
+  float* pool = (float*)(ws + L.pool);
+  float* fc = (float*)(ws + L.fc);
+  const int c0 = P.cin0;
+  int rc = MIMAMO_OK;
+  for (int m0 = 0; m0 < M && !rc; m0 += P.chunk) {
+    const int Mc = M - m0 < P.chunk ? M - m0 : P.chunk;
+    void* a0 = ws + L.a0; void* a1 = ws + L.a1; void* cat = ws + L.cat; void* a2 = ws + L.a2;
+    void* a3 = ws + L.a3; void* a4 = ws + L.a4; void* a5 = ws + L.a5;
+    rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
+    if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
+    if (!rc) rc = conv_forward(P.conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
+    if (!rc) rc = conv_forward(P.conv[1], a1, Mc, 48, 48, cat, 128, nullptr, 0, s);      // -> cat[..., 0:64], 24x24
+    if (!rc) rc = conv_forward(P.conv[2], cat, Mc, 24, 24, a2, 128, nullptr, 0, s);
+    if (!rc) rc = conv_forward(P.conv[3], a2, Mc, 24, 24, a3, 128, nullptr, 0, s);       // 12x12
+    if (!rc) rc = conv_forward(P.conv[4], a3, Mc, 12, 12, a4, 256, nullptr, 0, s);
+    if (!rc) rc = conv_forward(P.conv[5], a4, Mc, 12, 12, a5, 256, nullptr, 0, s);       // 6x6
+    if (!rc) rc = avgpool_to_f32(a5, Mc, 36, 256, pool + (size_t)m0 * 256, 256, 0, kHeadElem, s);
+  }
+  if (!rc) rc = linear_forward(P.fc0, pool, 256, M, fc, 256, s);
+  if (!rc) rc = linear_forward(P.fc4, fc, 256, M, out, ldo, s);
+  return rc;
+}
+
 extern "C" void mimamo_head_destroy(mimamo_head* h) {
   if (!h) return;
-  for (auto& c : h->conv) conv_layer_free(c);
-  linear_free(h->mlp1); linear_free(h->mlp2); linear_free(h->fc0); linear_free(h->fc4);
+  mlp_free(h->mlp);
+  phasenet_free(h->pn);
   linear_free(h->transform); linear_free(h->xproj[0]); linear_free(h->xproj[1]); linear_free(h->classifier);
   for (int l = 0; l < 2; ++l) { cudaFree(h->whhT[l]); cudaFree(h->bhh[l]); }
   delete h;
@@ -71,31 +207,12 @@ extern "C" void mimamo_head_destroy(mimamo_head* h) {
 extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_phase,
                                   mimamo_head** head_out) {
   MM_REQUIRE(tensors && head_out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
-  MM_REQUIRE(num_phase == 12, MIMAMO_E_RUNTIME, "only num_phase=12 (24 phase channels) is supported");
+  MM_REQUIRE(num_phase >= 1 && num_phase <= 32, MIMAMO_E_RUNTIME, "num_phase must be in [1,32] (2*num_phase phase channels), got %d", num_phase);
   TensorTable T{tensors, n_tensors};
   mimamo_head* h = new mimamo_head();
-  h->num_phase = num_phase; h->cin0 = 2 * num_phase;
-  { const char* e = getenv("MIMAMO_HEAD_CHUNK"); if (e && atoi(e) > 0) h->conv_chunk = atoi(e); }
-  const int c0 = h->cin0;
-  int rc = make_linear(T, "mlp.mlp.1", "mlp.mlp.2", 256, 2048, 1, true, h->mlp1);
-  if (!rc) rc = make_linear(T, "mlp.mlp.5", "mlp.mlp.6", 256, 256, 1, true, h->mlp2);
-  const int chans[3][2] = {{c0, 64}, {c0 + 64, 128}, {128, 256}};
-  for (int b = 0; b < 3 && !rc; ++b) {
-    char p[64];
-    snprintf(p, sizeof(p), "phasenet.conv_net.%d.", b);
-    const std::string pre(p);
-    rc = make_phase_conv(T, pre + "0", pre + "1", chans[b][1], chans[b][0], 1, h->conv[2 * b]);
-    if (!rc) rc = make_phase_conv(T, pre + "3", pre + "4", chans[b][1], chans[b][1], 2, h->conv[2 * b + 1]);
-  }
-  {
-    const char* e = getenv("MIMAMO_HEAD_CALIB");
-    if (!(e && e[0] == '0')) {
-      const int relu_in[6] = {0, 64, 64, 128, 128, 256};     // post-ReLU input channels of conv_net.{0,1,2}.{0,3}
-      for (int i = 1; i < 6 && !rc; ++i) rc = compensate_phase_conv(h->conv[i], relu_in[i]);
-    }
-  }
-  if (!rc) rc = make_linear(T, "phasenet.fc.0", "phasenet.fc.2", 256, 256, 1, false, h->fc0);
-  if (!rc) rc = make_linear(T, "phasenet.fc.4", "phasenet.fc.6", 256, 256, 1, false, h->fc4);
+  h->num_phase = num_phase;
+  int rc = mlp_init(T, "mlp.mlp.", h->mlp);
+  if (!rc) rc = phasenet_init(T, "phasenet.", 2 * num_phase, h->pn);
   if (!rc) rc = make_linear(T, "transform.0", "transform.2", 256, 512, 1, false, h->transform);
   if (!rc) rc = make_linear(T, "classifier.1", "classifier.2", 2, 256, 0, true, h->classifier);
   for (int l = 0; l < 2 && !rc; ++l) {
@@ -125,28 +242,18 @@ extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_t
 }
 
 namespace {
-struct HeadLayout {
-  size_t feat, f2, xp, y0, y1, pool, fc, a0, a1, cat, a2, a3, a4, a5, total;
-};
+struct HeadLayout { size_t feat, f2, xp, y0, y1, mlp_tmp, pn, total; };
 HeadLayout head_layout(const mimamo_head* h, int M) {
   HeadLayout L;
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t at = cur; cur += align_up(bytes, 1024); return at; };
-  const size_t Mc = (size_t)(M < h->conv_chunk ? M : h->conv_chunk);
   L.feat = take((size_t)M * 512 * 4);
   L.f2 = take((size_t)M * 256 * 4);
   L.xp = take((size_t)M * 768 * 4);
   L.y0 = take((size_t)M * 256 * 4);
   L.y1 = take((size_t)M * 256 * 4);
-  L.pool = take((size_t)M * 256 * 4);
-  L.fc = take((size_t)M * 256 * 4);
-  L.a0 = take(Mc * 48 * 48 * 64 * 2);     // phase_0 as NHWC (24 -> 64 channels)
-  L.a1 = take(Mc * 48 * 48 * 64 * 2);     // conv_net[0][0]
-  L.cat = take(Mc * 24 * 24 * 128 * 2);   // [conv_net[0][3] (64) | phase_1 (24) | zero pad]
-  L.a2 = take(Mc * 24 * 24 * 128 * 2);    // conv_net[1][0]
-  L.a3 = take(Mc * 12 * 12 * 128 * 2);    // conv_net[1][3]
-  L.a4 = take(Mc * 12 * 12 * 256 * 2);    // conv_net[2][0]
-  L.a5 = take(Mc * 6 * 6 * 256 * 2);      // conv_net[2][3]
+  L.mlp_tmp = take(mlp_tmp_floats(h->mlp, M) * 4);
+  L.pn = take(phasenet_layout(h->pn, M).total);
   L.total = cur + 1024;
   return L;
 }
@@ -168,29 +275,11 @@ extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, c
   MM_REQUIRE(workspace && workspace_bytes >= L.total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", L.total);
   char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   float* feat = (float*)(ws + L.feat); float* f2 = (float*)(ws + L.f2); float* xp = (float*)(ws + L.xp);
-  float* y0 = (float*)(ws + L.y0); float* y1 = (float*)(ws + L.y1); float* pool = (float*)(ws + L.pool);
-  float* fc = (float*)(ws + L.fc);
+  float* y0 = (float*)(ws + L.y0); float* y1 = (float*)(ws + L.y1);
   // spatial stream: MLP over the ResNet50 features -> feat[:, 0:256]
-  int rc = linear_forward(h->mlp1, rgb, 2048, M, f2, 256, s);
-  if (!rc) rc = linear_forward(h->mlp2, f2, 256, M, feat, 512, s);
+  int rc = mlp_run(h->mlp, rgb, M, feat, 512, (float*)(ws + L.mlp_tmp), s);
   // temporal stream: PhaseNet -> feat[:, 256:512]
-  const int c0 = h->cin0;
-  for (int m0 = 0; m0 < M && !rc; m0 += h->conv_chunk) {
-    const int Mc = M - m0 < h->conv_chunk ? M - m0 : h->conv_chunk;
-    void* a0 = ws + L.a0; void* a1 = ws + L.a1; void* cat = ws + L.cat; void* a2 = ws + L.a2;
-    void* a3 = ws + L.a3; void* a4 = ws + L.a4; void* a5 = ws + L.a5;
-    rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
-    if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
-    if (!rc) rc = conv_forward(h->conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
-    if (!rc) rc = conv_forward(h->conv[1], a1, Mc, 48, 48, cat, 128, nullptr, 0, s);      // -> cat[..., 0:64], 24x24
-    if (!rc) rc = conv_forward(h->conv[2], cat, Mc, 24, 24, a2, 128, nullptr, 0, s);
-    if (!rc) rc = conv_forward(h->conv[3], a2, Mc, 24, 24, a3, 128, nullptr, 0, s);       // 12x12
-    if (!rc) rc = conv_forward(h->conv[4], a3, Mc, 12, 12, a4, 256, nullptr, 0, s);
-    if (!rc) rc = conv_forward(h->conv[5], a4, Mc, 12, 12, a5, 256, nullptr, 0, s);       // 6x6
-    if (!rc) rc = avgpool_to_f32(a5, Mc, 36, 256, pool + (size_t)m0 * 256, 256, 0, kHeadElem, s);
-  }
-  if (!rc) rc = linear_forward(h->fc0, pool, 256, M, fc, 256, s);
-  if (!rc) rc = linear_forward(h->fc4, fc, 256, M, feat + 256, 512, s);
+  if (!rc) rc = phasenet_run(h->pn, phase_0, phase_1, M, feat + 256, 512, ws + L.pn, s);
   // fusion + recurrence over dim 0 (= bs; the nf frames are the GRU batch)
   if (!rc) rc = linear_forward(h->transform, feat, 512, M, f2, 256, s);
   if (!rc) rc = linear_forward(h->xproj[0], f2, 256, M, xp, 768, s);
@@ -198,5 +287,67 @@ extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, c
   if (!rc) rc = linear_forward(h->xproj[1], y0, 256, M, xp, 768, s);
   if (!rc) rc = gru_layer(xp, h->whhT[1], h->bhh[1], bs, nf, 128, y1, s);
   if (!rc) rc = linear_forward(h->classifier, y1, 256, M, out, 2, s);
+  return rc;
+}
+
+// ---- the two streams on their own: MLP.forward / PhaseNet.forward (api/mimamo_net.py:22-26,79-95) ----
+extern "C" void mimamo_mlp_destroy(mimamo_mlp* m) { if (m) { mlp_free(m->p); delete m; } }
+extern "C" int mimamo_mlp_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, mimamo_mlp** out) {
+  MM_REQUIRE(tensors && out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
+  TensorTable T{tensors, n_tensors};
+  mimamo_mlp* m = new mimamo_mlp();
+  const int rc = mlp_init(T, "mlp.", m->p);
+  if (rc) { mimamo_mlp_destroy(m); return rc; }
+  *out = m;
+  return MIMAMO_OK;
+}
+extern "C" int mimamo_mlp_workspace_bytes(const mimamo_mlp* m, int32_t rows, size_t* bytes_out) {
+  MM_REQUIRE(m && bytes_out && rows >= 0, MIMAMO_E_VALUE, "bad arguments");
+  *bytes_out = mlp_tmp_floats(m->p, rows) * 4 + 256;
+  return MIMAMO_OK;
+}
+extern "C" int mimamo_mlp_in_features(const mimamo_mlp* m) { return m ? m->p.in_f : 0; }
+extern "C" int mimamo_mlp_forward(const mimamo_mlp* m, const float* x, int32_t rows, float* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  MM_REQUIRE(m && x && out && rows >= 0, MIMAMO_E_VALUE, "bad arguments");
+  if (rows == 0) return MIMAMO_OK;
+  size_t need = 0;
+  mimamo_mlp_workspace_bytes(m, rows, &need);
+  MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
+  float* tmp = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  return mlp_run(m->p, x, rows, out, 256, tmp, (cudaStream_t)stream);
+}
+
+extern "C" void mimamo_phasenet_destroy(mimamo_phasenet* n) { if (n) { phasenet_free(n->p); delete n; } }
+extern "C" int mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_channels,
+                                      mimamo_phasenet** out) {
+  MM_REQUIRE(tensors && out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
+  TensorTable T{tensors, n_tensors};
+  mimamo_phasenet* n = new mimamo_phasenet();
+  const int rc = phasenet_init(T, "", num_channels, n->p);
+  if (rc) { mimamo_phasenet_destroy(n); return rc; }
+  *out = n;
+  return MIMAMO_OK;
+}
+extern "C" int mimamo_phasenet_workspace_bytes(const mimamo_phasenet* n, int32_t rows, size_t* bytes_out) {
+  MM_REQUIRE(n && bytes_out && rows >= 0, MIMAMO_E_VALUE, "bad arguments");
+  *bytes_out = phasenet_layout(n->p, rows > 0 ? rows : 1).total + align_up((size_t)(rows > 0 ? rows : 1) * 256 * 4, 1024) + 2048;
+  return MIMAMO_OK;
+}
+// feature != 0: out f32[rows,256] (the fc stack); feature == 0: out f32[rows,1] (+ Linear(256,1) + BatchNorm1d(1))
+extern "C" int mimamo_phasenet_forward(const mimamo_phasenet* n, const float* phase_0, const float* phase_1, int32_t rows,
+                                       int32_t feature, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  MM_REQUIRE(n && phase_0 && phase_1 && out && rows >= 0, MIMAMO_E_VALUE, "bad arguments");
+  if (rows == 0) return MIMAMO_OK;
+  MM_REQUIRE(feature || n->p.has_cls, MIMAMO_E_VALUE, "this PhaseNet was created without classifier weights");
+  size_t need = 0;
+  mimamo_phasenet_workspace_bytes(n, rows, &need);
+  MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
+  char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  const size_t pn_bytes = phasenet_layout(n->p, rows).total;
+  float* feat = reinterpret_cast<float*>(ws + pn_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = phasenet_run(n->p, phase_0, phase_1, rows, feature ? out : feat, 256, ws, s);
+  if (!rc && !feature) rc = linear_forward(n->p.cls, feat, 256, rows, out, 1, s);
   return rc;
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ float unwrap_correction(float dd) {
 
 __global__ void __launch_bounds__(kTailThreads, 2)
 phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, double* __restrict__ partial,
-                  const TailGeom g, const int* __restrict__ root, int nb, int coeff_T, int polar) {
+                  const TailGeom g, const int* __restrict__ root, int nb, int coeff_T, int polar, int mode) {
   extern __shared__ __align__(16) unsigned char raw[];
   const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp;
   const int n_in = rin * cin, n_out = trp * tcp;
@@ -77,8 +77,13 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
   float* hmg = hmp + rin * tcp;
   float* blur_prev = hmg + rin * tcp;                            // [trp][tcp]
   float* delta = blur_prev + n_out;                              // [trp][tcp]
-  __shared__ double red[kTailThreads / 32];
-  __shared__ float mean_s;
+  __shared__ double red[2][kTailThreads / 32];
+  __shared__ float mean_s[2];
+  // Output maps per (window, band): mode 0 = the T-1 phase differences (Phase_Difference_Extractor.extract); mode 1 = the
+  // T denoised phases, spatial mean removed (extract_phase(return_phase=True), Aff-wild-exps/utils.py:408-418); mode 2 =
+  // extract_phase(return_both=True): 2(T-1) slots of which insert_tensors (utils.py:419-432) fills only the first T-1,
+  // slot i = difference i/2 (i even) or denoised phase 1 + i/2 (i odd); the rest stay zero (cleared by the launcher).
+  const int n_slots = mode == 0 ? g.T - 1 : (mode == 1 ? g.T : 2 * (g.T - 1));
 
   const long long map = blockIdx.x;
   const int tile = blockIdx.y;
@@ -181,7 +186,7 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
     }
     __syncthreads();
     // (C) column pass (4 vertically adjacent outputs per thread), ratio, temporal difference
-    double part = 0.0;
+    double part = 0.0, part_ph = 0.0;
     {
       const int ygroups = trp >> 2;
       DivMod ic;
@@ -210,48 +215,73 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
               part += (double)dl;
             }
             blur_prev[cell] = val;
+            part_ph += (double)val;
           }
         }
       }
     }
-    if (t > 0) {
+    // which output slots this frame feeds: the difference (t-1, t) and / or the denoised phase of frame t
+    int slot_d = -1, slot_p = -1;
+    if (mode == 0) { if (t > 0) slot_d = t - 1; }
+    else if (mode == 1) slot_p = t;
+    else if (t > 0) {
+      if (2 * (t - 1) < g.T - 1) slot_d = 2 * (t - 1);
+      if (2 * (t - 1) + 1 < g.T - 1) slot_p = 2 * (t - 1) + 1;
+    }
+    if (slot_d >= 0 || slot_p >= 0) {
       part = warp_sum(part);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+      part_ph = warp_sum(part_ph);
+      if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = part; red[1][threadIdx.x >> 5] = part_ph; }
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (threadIdx.x < 2) {
+        const int which = threadIdx.x, slot = which == 0 ? slot_d : slot_p;
         double tot = 0.0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
-        if (single) mean_s = (float)(tot / (double)plane);
-        else partial[((size_t)map * (g.T - 1) + (t - 1)) * ntiles + tile] = tot;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[which][i];
+        if (single) mean_s[which] = (float)(tot / (double)plane);
+        else if (slot >= 0) partial[((size_t)map * n_slots + slot) * ntiles + tile] = tot;
       }
       __syncthreads();
-      const float mean = single ? mean_s : 0.f;
       const float lim = 15.7079632679489656f;                    // 5*pi
-      float* dst = out + ((size_t)map * (g.T - 1) + (t - 1)) * plane;
-      DivMod iw;
-      iw.init(threadIdx.x, tw);
-      for (int i = threadIdx.x; i < th * tw; i += blockDim.x, iw.step(w_sq, w_sr, tw)) {
-        const int y = iw.q, x = iw.r;
-        float v = delta[y * tcp + x];
-        if (single) v = fminf(fmaxf(__fsub_rn(v, mean), -lim), lim);
-        dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
+      for (int which = 0; which < 2; ++which) {
+        const int slot = which == 0 ? slot_d : slot_p;
+        if (slot < 0) continue;
+        const float mean = single ? mean_s[which] : 0.f;
+        const float* srcv = which == 0 ? delta : blur_prev;
+        float* dst = out + ((size_t)map * n_slots + slot) * plane;
+        DivMod iw;
+        iw.init(threadIdx.x, tw);
+        for (int i = threadIdx.x; i < th * tw; i += blockDim.x, iw.step(w_sq, w_sr, tw)) {
+          const int y = iw.q, x = iw.r;
+          float v = srcv[y * tcp + x];
+          if (single) {
+            v = __fsub_rn(v, mean);
+            if (which == 0) v = fminf(fmaxf(v, -lim), lim);
+          }
+          dst[(size_t)(y0 + y) * g.cols + x0 + x] = v;
+        }
       }
     }
     __syncthreads();
   }
 }
 
-// Tiled maps only: subtract the map mean (fixed-order sum of the tile partials) and clamp.
+// Tiled maps only: subtract the map mean (fixed-order sum of the tile partials) and clamp the differences.
 __global__ void phase_tail_finish_kernel(float* __restrict__ out, const double* __restrict__ partial,
-                                         int ntiles, long long plane) {
-  const long long m = blockIdx.x;                       // (map, t) index
+                                         int ntiles, long long plane, int n_slots, int active_slots, int mode) {
+  const long long m = blockIdx.x;                       // (map, slot) index
+  const int slot = (int)(m % n_slots);
+  if (slot >= active_slots) return;                     // return_both: the slots insert_tensors never fills stay zero
+  const bool clamp = mode == 0 || (mode == 2 && (slot & 1) == 0);
   double tot = 0.0;
   for (int i = 0; i < ntiles; ++i) tot += partial[m * ntiles + i];
   const float mean = (float)(tot / (double)plane);
   const float lim = 15.7079632679489656f;
   float* p = out + m * plane;
-  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.y * blockDim.x)
-    p[i] = fminf(fmaxf(__fsub_rn(p[i], mean), -lim), lim);
+  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.y * blockDim.x) {
+    float v = __fsub_rn(p[i], mean);
+    if (clamp) v = fminf(fmaxf(v, -lim), lim);
+    p[i] = v;
+  }
 }
 
 static TailGeom make_geom(int T, int rows, int cols) {
@@ -287,7 +317,7 @@ static int tail_setup() {
 
 int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, float* out,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream, const int* root = nullptr,
-                         int nb = 1, int coeff_T = 0, int polar = 0) {
+                         int nb = 1, int coeff_T = 0, int polar = 0, int mode = 0) {
   MM_REQUIRE(coeff && out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "phase_extract needs T >= 2 frames and a non-empty map");
   if (n_maps == 0) return MIMAMO_OK;
@@ -295,18 +325,22 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   if (rc) return rc;
   const TailGeom g = make_geom(T, rows, cols);
   const int ntiles = g.tiles_r * g.tiles_c;
+  const int n_slots = mode == 0 ? T - 1 : (mode == 1 ? T : 2 * (T - 1));
   size_t need = 0;
-  if (ntiles > 1) need = (size_t)n_maps * (T - 1) * ntiles * sizeof(double);
+  if (ntiles > 1) need = (size_t)n_maps * n_slots * ntiles * sizeof(double);
+  MM_REQUIRE(mode >= 0 && mode <= 2, MIMAMO_E_VALUE, "phase_extract mode must be 0, 1 or 2");
   MM_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
   const int threads = g.tile_r * g.tile_c >= 1600 ? kTailThreads : (g.tile_r * g.tile_c >= 400 ? 256 : 128);   // small maps: fewer idle threads per barrier
-  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T, polar);
+  if (mode == 2) MM_CUDA(cudaMemsetAsync(out, 0, (size_t)n_maps * n_slots * rows * cols * sizeof(float), stream));
+  phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T, polar, mode);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
     const long long plane = (long long)rows * cols;
-    dim3 fgrid((unsigned)(n_maps * (T - 1)), (unsigned)((plane + 4095) / 4096));
-    phase_tail_finish_kernel<<<fgrid, 256, 0, stream>>>(out, (const double*)workspace, ntiles, plane);
+    MM_REQUIRE(n_maps * n_slots < (1ll << 31), MIMAMO_E_VALUE, "batch too large for one launch");
+    dim3 fgrid((unsigned)(n_maps * n_slots), (unsigned)((plane + 4095) / 4096));
+    phase_tail_finish_kernel<<<fgrid, 256, 0, stream>>>(out, (const double*)workspace, ntiles, plane, n_slots, mode == 2 ? T - 1 : n_slots, mode);
     MM_LAUNCH_OK();
   }
   return MIMAMO_OK;
@@ -351,13 +385,20 @@ extern "C" int mimamo_phase_extract_workspace_bytes(int64_t n_maps, int32_t T, i
   MM_REQUIRE(bytes_out && T >= 2 && rows >= 1 && cols >= 1 && n_maps >= 0, MIMAMO_E_VALUE, "bad geometry");
   const TailGeom g = make_geom(T, rows, cols);
   const int ntiles = g.tiles_r * g.tiles_c;
-  *bytes_out = ntiles > 1 ? (size_t)n_maps * (T - 1) * ntiles * sizeof(double) : 0;
+  *bytes_out = ntiles > 1 ? (size_t)n_maps * (2 * (T - 1) > T ? 2 * (T - 1) : T) * ntiles * sizeof(double) : 0;   // covers every output mode
   return MIMAMO_OK;
 }
 
 extern "C" int mimamo_phase_extract(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols,
                                     float* out, void* workspace, size_t workspace_bytes, void* stream) {
   return phase_extract_launch(coeff, n_maps, T, rows, cols, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// The training-side variants (Steerable_Pyramid_Phase.extract_phase, Aff-wild-exps/utils.py:367-432): mode 1 = return_phase
+// -> out f32[n_maps, T, rows, cols], mode 2 = return_both -> out f32[n_maps, 2(T-1), rows, cols]; mode 0 = mimamo_phase_extract.
+extern "C" int mimamo_phase_extract_ex(const float* coeff, int64_t n_maps, int32_t T, int32_t rows, int32_t cols, int32_t mode,
+                                       float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return phase_extract_launch(coeff, n_maps, T, rows, cols, out, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 1, 0, 0, mode);
 }
 
 // ---- exact frame de-duplication -----------------------------------------------------------------

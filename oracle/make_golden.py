@@ -56,6 +56,45 @@ def head_case(R, name, bs, nf, seed):
     print(name, tuple(y.shape), chk, wchk)
 
 
+def scf_case(R, name, size, height, nbands, seed):
+    """SCFpyr_PyTorch.build / reconstruct of un-mirrored images (api/steerable/SCFpyr_PyTorch.py:70-125,214-245)."""
+    x = torch.rand(2, 1, size, size, generator=torch.Generator().manual_seed(seed))
+    pyr = R.SCFpyr_PyTorch(height=height, nbands=nbands, scale_factor=2, device=torch.device("cpu"))
+    coeff = pyr.build(x)
+    rec = pyr.reconstruct(coeff)
+    mine = O.pyramid_build(x, height, nbands)
+    out = {"x": x.numpy(), "height": height, "nbands": nbands, "rec": rec.numpy()}
+    for i, (a, b) in enumerate(zip(coeff, mine)):
+        if isinstance(a, list):
+            for j, (aa, bb) in enumerate(zip(a, b)):
+                assert torch.equal(aa, bb), "oracle pyramid_build drifted from the reference (%s)" % name
+            out["c%d" % i] = torch.stack(a, 0).numpy()
+        else:
+            assert torch.equal(a, b), "oracle pyramid_build drifted from the reference (%s)" % name
+            out["c%d" % i] = a.numpy()
+    mine_rec = O.pyramid_reconstruct(coeff, nbands)
+    assert (mine_rec - rec).abs().max() < 1e-6, "oracle pyramid_reconstruct drifted from the reference (%s)" % name
+    print(name, "levels", len(coeff), "round trip max|err| %.2e" % (rec - x[:, 0]).abs().max().item(),
+          "oracle reconstruct vs reference %.1e" % (mine_rec - rec).abs().max().item())
+    np.savez(os.path.join(GOLD, name + ".npz"), **out)
+
+
+def extract_phase_case(R, name, seed):
+    """Steerable_Pyramid_Phase.extract_phase(return_phase / return_both), Aff-wild-exps/utils.py:367-432."""
+    U = ref_shim.load_training_utils()
+    x = torch.rand(2, 5, 32, 32, generator=torch.Generator().manual_seed(seed))
+    spp = U.Steerable_Pyramid_Phase(height=4, nbands=2, scale_factor=2, device=torch.device("cpu"), extract_level=2)
+    coeff = spp.build_pyramid(x)
+    outs = {"diff": spp.extract_phase(coeff), "phase": spp.extract_phase(coeff, return_phase=True),
+            "both": spp.extract_phase(coeff, return_both=True)}
+    mine = {"diff": O.extract_phase(coeff), "phase": O.extract_phase(coeff, return_phase=True),
+            "both": O.extract_phase(coeff, return_both=True)}
+    for k in outs:
+        assert torch.equal(outs[k], mine[k]), "oracle extract_phase(%s) drifted from the reference" % k
+    np.savez(os.path.join(GOLD, name + ".npz"), coeff=coeff.numpy(), **{k: v.numpy() for k, v in outs.items()})
+    print(name, {k: tuple(v.shape) for k, v in outs.items()})
+
+
 def main():
     R = ref_shim.load()
     os.makedirs(GOLD, exist_ok=True)
@@ -69,6 +108,11 @@ def main():
     # head: GRU recurs over dim 0 (bs) -- bs=3 exercises the recurrence, bs=1 the degenerate case
     head_case(R, "head_b3", 3, 4, seed=5)
     head_case(R, "head_b1", 1, 8, seed=6)
+    # full pyramid of un-mirrored images + reconstruction: two oriented levels; an odd level size (50 -> 25)
+    scf_case(R, "scf_64", 64, 4, 2, seed=7)
+    scf_case(R, "scf_50", 50, 3, 3, seed=8)
+    # training-side tail variants
+    extract_phase_case(R, "extract_phase", seed=9)
     # unwrap known answers straight from the reference function
     pu = R.phase_utils
     kat_in = torch.tensor([[2.0, -2.5, -2.6], [-2.0, 2.5, 2.6], [0.0, 3.0, -3.0], [3.0, -3.0, 3.0]])

@@ -160,6 +160,53 @@ def pyramid_build(images: torch.Tensor, height: int, nbands: int,
     return coeff
 
 
+def pyramid_reconstruct(coeff: List, nbands: int, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """SCFpyr_PyTorch.reconstruct + _reconstruct_levels, api/steerable/SCFpyr_PyTorch.py:214-314.
+
+    coeff as returned by pyramid_build -> images (N,S,S).  Reconstruction uses its own angular LUT
+    (sqrt(const) cos^order, no half-plane indicator, :266-268) and the factor (i)^(nbands-1) (:65,284-287)."""
+    if nbands != len(coeff[1]):
+        raise Exception("Unmatched number of orientations")
+    rows, cols = coeff[0].shape[1], coeff[0].shape[2]
+    cdtype = torch.complex64 if dtype == torch.float32 else torch.complex128
+    log_rad, angle = polar_grid(cols, rows)
+    xr, yr = raised_cosine(1, -0.5)
+    yr = np.sqrt(yr)
+    yir = np.sqrt(np.abs(1 - yr ** 2))
+    as_t = lambda m: torch.from_numpy(m).to(dtype)[None]
+    lutsize = 1024
+    xcosn = np.pi * np.arange(-(2 * lutsize + 1), lutsize + 2) / lutsize
+    order = nbands - 1
+    const = (2 ** (2 * order)) * (math.factorial(order) ** 2) / (nbands * math.factorial(2 * order))
+    ycosn = np.sqrt(const) * np.cos(xcosn) ** order
+    twist = complex(0, 1) ** (nbands - 1)
+
+    def levels(cf, log_rad, angle, xr):
+        if len(cf) == 1:
+            return _shift(torch.fft.fft2(cf[0].to(dtype)).to(cdtype))
+        xr = xr - 1.0
+        himask = as_t(lut(log_rad, yr, xr))
+        orient = torch.zeros(cf[0][0].shape[:-1], dtype=cdtype)
+        for b in range(nbands):
+            anglemask = as_t(lut(angle, ycosn, xcosn + np.pi * b / nbands))
+            band = torch.view_as_complex(cf[0][b].to(dtype).contiguous()).to(cdtype)
+            banddft = _shift(torch.fft.fft2(band)) * anglemask * himask
+            orient = orient + torch.complex(twist.real * banddft.real - twist.imag * banddft.imag,
+                                            twist.real * banddft.imag + twist.imag * banddft.real)
+        (r0, r1), (c0, c1) = crop_bounds(log_rad.shape[0]), crop_bounds(log_rad.shape[1])
+        nlog_rad, nangle = log_rad[r0:r1, c0:c1], angle[r0:r1, c0:c1]
+        lomask = as_t(lut(nlog_rad, yir, xr))
+        nres = levels(cf[1:], nlog_rad, nangle, xr)
+        res = torch.zeros_like(orient)
+        res[:, r0:r1, c0:c1] = nres * lomask
+        return res + orient
+
+    temp = levels(coeff[1:], log_rad, angle, xr)
+    hidft = _shift(torch.fft.fft2(coeff[0].to(dtype)).to(cdtype))
+    out = temp * as_t(lut(log_rad, yir, xr)) + hidft * as_t(lut(log_rad, yr, xr))
+    return torch.fft.ifft2(_unshift(out)).real
+
+
 def build_pyramid(im_batch: torch.Tensor, height: int, nbands: int, extract_level,
                   symmetry: bool = True, dtype: torch.dtype = torch.float32):
     """Phase_Difference_Extractor.build_pyramid, api/phase_difference_extractor.py:38-87.
@@ -235,6 +282,32 @@ def extract(coeff: torch.Tensor) -> torch.Tensor:
     delta = smooth[:, :, 1:] - smooth[:, :, :-1]
     delta = delta - delta.mean(-1).mean(-1)[..., None, None]
     return torch.clamp(delta, -5 * math.pi, 5 * math.pi)
+
+
+def extract_phase(coeff: torch.Tensor, return_phase: bool = False, return_both: bool = False) -> torch.Tensor:
+    """Steerable_Pyramid_Phase.extract_phase, Aff-wild-exps/utils.py:367-418 (the training-side superset of `extract`).
+
+    coeff (bs,nb,T,w,h,2).  default -> phase differences (bs,nb,T-1,w,h) (same as `extract`); return_phase ->
+    denoised phase minus its spatial mean (bs,nb,T,w,h); return_both -> insert_tensors(differences, phases[:, :, 1:])
+    (bs,nb,2(T-1),w,h), where insert_tensors (:419-432) loops over range(T-1) only: slot i < T-1 holds difference i//2
+    (i even) or phase 1 + i//2 (i odd) and the remaining T-1 slots stay zero -- kept bug for bug."""
+    bs, nb, t, w, h, _ = coeff.shape
+    re, im = coeff[..., 0], coeff[..., 1]
+    phase = torch.atan2(im, re).reshape(bs * nb, t, w, h)
+    mag = torch.sqrt(im ** 2 + re ** 2).reshape(bs * nb, t, w, h) + 1e-10
+    phase = unwrap_positive_jumps(phase, dim=-3)
+    smooth = amplitude_weighted_blur(mag, phase, torch.from_numpy(gaussian_taps(2, 11))).view(bs, nb, t, w, h)
+    delta = smooth[:, :, 1:] - smooth[:, :, :-1]
+    smooth = smooth - smooth.mean(-1).mean(-1)[..., None, None]
+    delta = delta - delta.mean(-1).mean(-1)[..., None, None]
+    delta = torch.clamp(delta, -5 * math.pi, 5 * math.pi)
+    if return_both:
+        rest = smooth[:, :, 1:]
+        out = torch.zeros(bs, nb, 2 * (t - 1), w, h, dtype=delta.dtype)
+        for i in range(t - 1):
+            out[:, :, i] = delta[:, :, i // 2] if i % 2 == 0 else rest[:, :, i // 2]
+        return out
+    return smooth if return_phase else delta
 
 
 def phase_diff_output(phase_batch: torch.Tensor, height: int = 4, nbands: int = 2,
@@ -322,31 +395,46 @@ def _gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse):
     return out
 
 
+def mlp_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "mlp.mlp.") -> torch.Tensor:
+    """MLP.forward in eval mode, api/mimamo_net.py:6-26: (rows, features) -> (rows, 256); [Dropout, Linear, BN, ReLU]
+    per hidden layer (keys 4i+1 / 4i+2 of the nn.Sequential), any depth."""
+    i = 0
+    while prefix + "%d.weight" % (4 * i + 1) in sd:
+        lin, bn = prefix + str(4 * i + 1), prefix + str(4 * i + 2)
+        x = F.relu(_bn(F.linear(x, sd[lin + ".weight"], sd[lin + ".bias"]), sd, bn))
+        i += 1
+    return x
+
+
+def phasenet_forward(sd: Dict[str, torch.Tensor], l0: torch.Tensor, l1: torch.Tensor, prefix: str = "phasenet.",
+                     feature: bool = True) -> torch.Tensor:
+    """PhaseNet.forward in eval mode for 48x48 inputs, api/mimamo_net.py:79-95: (rows,C,48,48), (rows,C,24,24) ->
+    (rows,256) when `feature`, else (rows,1) after the classifier Linear(256,1) + BatchNorm1d(1, eps=1e-6) (:62-64)."""
+    def conv_block(t, blk, stride2):
+        p = prefix + "conv_net.%d." % blk
+        t = F.relu(_bn(F.conv2d(t, sd[p + "0.weight"], sd[p + "0.bias"], padding=1), sd, p + "1"))
+        return F.relu(_bn(F.conv2d(t, sd[p + "3.weight"], sd[p + "3.bias"], padding=1, stride=stride2),
+                          sd, p + "4"))
+
+    t = torch.cat([conv_block(l0, 0, 2), l1], dim=1)
+    t = conv_block(conv_block(t, 1, 2), 2, 2)
+    t = F.avg_pool2d(t, kernel_size=t.shape[-1]).reshape(l0.shape[0], -1)
+    for lin, bn in ((0, 2), (4, 6)):                                            # fc: Linear, ReLU, BN, Dropout
+        t = _bn(F.relu(F.linear(t, sd[prefix + "fc.%d.weight" % lin], sd[prefix + "fc.%d.bias" % lin])),
+                sd, prefix + "fc.%d" % bn)
+    if feature:
+        return t
+    y = F.linear(t, sd[prefix + "classifier.0.weight"], sd[prefix + "classifier.0.bias"])
+    return _bn(y, sd, prefix + "classifier.1", eps=1e-6)
+
+
 def head_forward(sd: Dict[str, torch.Tensor], phase_0, phase_1, rgb) -> torch.Tensor:
     """Two_Stream_RNN.forward in eval mode, api/mimamo_net.py:129-143 (MLP :22-26,
     PhaseNet :79-95).  NOTE the GRU (built without batch_first, :119) recurs over dim 0 =
     the snippet axis, batch = frames."""
     bs, nf = rgb.shape[0], rgb.shape[1]
-    x = rgb.reshape(bs * nf, -1)
-    for lin, bn in ((1, 2), (5, 6)):                                            # mlp.mlp
-        x = F.relu(_bn(F.linear(x, sd["mlp.mlp.%d.weight" % lin], sd["mlp.mlp.%d.bias" % lin]),
-                       sd, "mlp.mlp.%d" % bn))
-    spatial = x
-
-    def conv_block(t, blk, stride2):
-        p = "phasenet.conv_net.%d." % blk
-        t = F.relu(_bn(F.conv2d(t, sd[p + "0.weight"], sd[p + "0.bias"], padding=1), sd, p + "1"))
-        return F.relu(_bn(F.conv2d(t, sd[p + "3.weight"], sd[p + "3.bias"], padding=1, stride=stride2),
-                          sd, p + "4"))
-
-    l0 = phase_0.reshape(bs * nf, *phase_0.shape[2:])
-    l1 = phase_1.reshape(bs * nf, *phase_1.shape[2:])
-    t = torch.cat([conv_block(l0, 0, 2), l1], dim=1)
-    t = conv_block(conv_block(t, 1, 2), 2, 2)
-    t = F.avg_pool2d(t, kernel_size=t.shape[-1]).reshape(bs * nf, -1)
-    for lin, bn in ((0, 2), (4, 6)):                                            # phasenet.fc
-        t = _bn(F.relu(F.linear(t, sd["phasenet.fc.%d.weight" % lin], sd["phasenet.fc.%d.bias" % lin])),
-                sd, "phasenet.fc.%d" % bn)
+    spatial = mlp_forward(sd, rgb.reshape(bs * nf, -1))
+    t = phasenet_forward(sd, phase_0.reshape(bs * nf, *phase_0.shape[2:]), phase_1.reshape(bs * nf, *phase_1.shape[2:]))
     feat = torch.cat([spatial, t], dim=-1)
     feat = _bn(F.relu(F.linear(feat, sd["transform.0.weight"], sd["transform.0.bias"])), sd, "transform.2")
     seq = feat.view(bs, nf, -1)

@@ -90,6 +90,37 @@ def install():
     _installed = True
 
 
+def load_training_utils():
+    """Aff-wild-exps/utils.py (home of Steerable_Pyramid_Phase, the training-side superset of the extractor) exec'd
+    under the shim: its two `cuda(async=True)` tokens (:253,275, functions not used here) are respelled so the file
+    parses, mpl_toolkits is stubbed, the blur kernel is cast to float32 as on the CUDA branch, and `Tensor.cuda()` (extract_phase's return_both ends in `.cuda()`, :406) is a
+    no-op on this GPU-less container.  No other change; `steerable` resolves to the reference's own api/steerable."""
+    install()
+    for name in ("mpl_toolkits", "mpl_toolkits.mplot3d"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+    for name, attr in (("matplotlib", "cm"), ("matplotlib", "pyplot")):
+        if not hasattr(sys.modules[name], attr):
+            setattr(sys.modules[name], attr, sys.modules.get("matplotlib." + attr, types.ModuleType(attr)))
+    src_path = os.path.join(REFERENCE_ROOT, "Aff-wild-exps", "utils.py")
+    with open(src_path) as fh:
+        text = fh.read().replace("cuda(async=True)", "cuda(non_blocking=True)")
+    mod = types.ModuleType("affwild_utils")
+    mod.__file__ = src_path
+    prev = torch.get_default_dtype()
+    exec(compile(text, src_path, "exec"), mod.__dict__)
+    torch.set_default_dtype(prev)
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        # amplitude_based_gaussian_blur (:245-257) casts its filters to float32 only on its CUDA branch (the only one the
+        # training code ever took); on this CPU-only container the float64 numpy kernel would reach F.conv2d next to
+        # float32 inputs and raise.  Hand it the same float32 values the CUDA branch computes with.
+        make_kernel = mod.gaussian_kernel
+        mod.gaussian_kernel = lambda *a, **k: make_kernel(*a, **k).astype(np.float32)
+    return mod
+
+
 def load():
     """Return the reference's hot-path symbols (unmodified code objects)."""
     install()

@@ -165,3 +165,51 @@ def test_end_to_end_batch32_grouping(cuda, dtype, monkeypatch):
     print("end-to-end B=32 grouping (%s ResNet): valence/arousal max|err| %.3e, mean %.3e" % (dtype, err.max().item(), err.mean().item()))
     assert out.shape == (B, Fr, 2)
     assert err.max().item() < (VA_TOL if dtype == "fp16" else 3e-2)
+
+
+def test_mlp_and_phasenet_on_their_own(cuda):
+    """MLP.forward / PhaseNet.forward (api/mimamo_net.py:22-26,79-95) as stand-alone modules, feature=True and the
+    classifier output (feature=False), and a deeper MLP than the published one."""
+    from mimamo_net import MLP, PhaseNet
+    gen = torch.Generator().manual_seed(41)
+    for hidden in ([2048, 256, 256], [512, 384, 320, 256]):
+        mlp = MLP(hidden).eval()
+        sd = O.synthetic_state_dict([(k, tuple(v.shape)) for k, v in mlp.state_dict().items()], seed=3)
+        mlp.load_state_dict(sd)
+        x = torch.rand(3, 5, hidden[0], generator=gen) * 2
+        got = mlp(x.to(cuda)).cpu()
+        ref = O.mlp_forward(sd, x.reshape(15, -1), prefix="mlp.").view(3, 5, 256)
+        err = (got - ref).abs().max().item()
+        print("MLP %s: max|err| %.2e" % (hidden, err))
+        assert got.shape == (3, 5, 256) and err < 1e-4
+    for feature in (True, False):
+        net = PhaseNet(48, 24, hidden_units=[256, 256, 1], dropout=0.3, feature=feature).eval()
+        sd = O.synthetic_state_dict([(k, tuple(v.shape)) for k, v in net.state_dict().items()], seed=4)
+        net.load_state_dict(sd)
+        p0 = torch.randn(2, 3, 24, 48, 48, generator=gen)
+        p1 = torch.randn(2, 3, 24, 24, 24, generator=gen)
+        got = net(p0.to(cuda), p1.to(cuda)).cpu()
+        ref = O.phasenet_forward(sd, p0.reshape(6, 24, 48, 48), p1.reshape(6, 24, 24, 24), prefix="", feature=feature)
+        err = (got - ref).abs().max().item()
+        print("PhaseNet feature=%s: max|err| %.2e (scale %.2f)" % (feature, err, ref.abs().max().item()))
+        assert got.shape == ref.shape and err < 2e-3 * max(1.0, ref.abs().max().item())
+    with pytest.raises(ValueError):
+        PhaseNet(50, 24)                                        # "Incorrect input size"
+
+
+def test_head_other_num_phase(cuda):
+    """Two_Stream_RNN(num_phase=8): 16 phase channels per level (the Tester passes its num_phase through, api/tester.py:42)."""
+    from mimamo_net import Two_Stream_RNN
+    gen = torch.Generator().manual_seed(43)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(num_phase=8), seed=2)
+    model = Two_Stream_RNN(num_phase=8).eval()
+    model.load_state_dict(sd)
+    p0 = torch.randn(3, 4, 16, 48, 48, generator=gen)
+    p1 = torch.randn(3, 4, 16, 24, 24, generator=gen)
+    rgb = torch.rand(3, 4, 2048, generator=gen) * 4
+    out = model([p0.to(cuda), p1.to(cuda)], rgb.to(cuda)).cpu()
+    with torch.no_grad():
+        ref = O.head_forward(sd, p0, p1, rgb)
+    err = (out - ref).abs().max().item()
+    print("head num_phase=8: max|err| %.3e" % err)
+    assert err < VA_TOL

@@ -168,3 +168,79 @@ def test_config3_large_frames(cuda):
         assert err.max() < PHASE_TOL
     with pytest.raises(RuntimeError, match="Cannot build 7 levels, image too small."):
         _pde(7, 8, [1]).build_pyramid(x.to(cuda))
+
+
+@pytest.mark.parametrize("name", ["scf_64", "scf_50"])
+def test_full_pyramid_build_and_reconstruct(cuda, golden_dir, name):
+    """SCFpyr_PyTorch.build (hi0, every band at full size, lo) and reconstruct through mimamo_scf_build /
+    mimamo_scf_reconstruct vs the unmodified reference's outputs, plus the round-trip property."""
+    from steerable.SCFpyr_PyTorch import SCFpyr_PyTorch
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = torch.from_numpy(g["x"]).to(cuda)
+    height, nbands = int(g["height"]), int(g["nbands"])
+    pyr = SCFpyr_PyTorch(height=height, nbands=nbands, scale_factor=2, device=cuda)
+    coeff = pyr.build(x)
+    assert isinstance(coeff, list) and len(coeff) == height
+    worst = 0.0
+    truth = O.pyramid_build(x.cpu().double(), height, nbands, dtype=torch.float64)
+    for i, c in enumerate(coeff):
+        ref = torch.from_numpy(g["c%d" % i])
+        got = torch.stack(c, 0).cpu() if isinstance(c, list) else c.cpu()
+        t64 = torch.stack(truth[i], 0) if isinstance(truth[i], list) else truth[i]
+        assert got.shape == ref.shape
+        scale = max(1.0, ref.abs().max().item())            # the low residual carries the image mean times (S/s)^2
+        e_ref = (got - ref).abs().max().item() / scale
+        print("  unit %d: |gpu-ref| %.2e  |gpu-fp64| %.2e  |ref-fp64| %.2e  (relative to %.1f)" % (
+            i, e_ref, (got.double() - t64).abs().max().item() / scale, (ref.double() - t64).abs().max().item() / scale, scale))
+        worst = max(worst, e_ref)
+    rec = pyr.reconstruct(coeff).cpu()
+    err_rec = (rec - torch.from_numpy(g["rec"])).abs().max().item()
+    err_rt = (rec - x[:, 0].cpu()).abs().max().item()
+    # the reference's own coefficients through the device reconstruct
+    ref_coeff = []
+    for i in range(height):
+        r = torch.from_numpy(g["c%d" % i]).to(cuda)
+        ref_coeff.append([r[b] for b in range(r.shape[0])] if r.dim() == 5 else r)
+    err_rec2 = (pyr.reconstruct(ref_coeff).cpu() - torch.from_numpy(g["rec"])).abs().max().item()
+    print("%s: build |gpu-ref| %.2e, reconstruct |gpu-ref| %.2e (ref coeff in: %.2e), round trip %.2e" % (name, worst, err_rec, err_rec2, err_rt))
+    assert worst < COEFF_TOL and err_rec < 1e-5 and err_rec2 < 1e-5 and err_rt < 2e-5
+    with pytest.raises(Exception):
+        pyr.reconstruct([coeff[0], coeff[1][:-1]] + coeff[2:])       # "Unmatched number of orientations"
+    with pytest.raises(RuntimeError):
+        SCFpyr_PyTorch(height=9, nbands=2, device=cuda).build(x)      # 'Cannot build 9 levels, image too small.'
+
+
+def test_build_pyramid_without_symmetry(cuda):
+    """symmetry=False: no mirror extension, no quadrant crop (api/phase_difference_extractor.py:38-45,76-86)."""
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    pde = _pde(4, 2, [1, 2])
+    got = pde.build_pyramid(x.to(cuda), symmetry=False)
+    ref = O.build_pyramid(x, 4, 2, [1, 2], symmetry=False)
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and (a.cpu() - b).abs().max().item() < COEFF_TOL
+    assert got[0].shape == (2, 2, 3, 64, 64, 2) and got[1].shape == (2, 2, 3, 32, 32, 2)
+    one = _pde(4, 2, 2).build_pyramid(x.to(cuda), symmetry=False)      # int extract_level -> a tensor
+    assert torch.equal(one, got[1])
+
+
+def test_extract_phase_variants(cuda, golden_dir):
+    """Steerable_Pyramid_Phase.extract_phase(return_phase / return_both) vs the reference's outputs,
+    on whole-map tiles (16x16) and on the tiled path (64x64 maps, fixed-order two-phase means)."""
+    from phase_difference_extractor import Steerable_Pyramid_Phase
+    g = np.load(os.path.join(golden_dir, "extract_phase.npz"))
+    spp = Steerable_Pyramid_Phase(height=4, nbands=2, scale_factor=2, device=cuda, extract_level=2)
+    coeff = torch.from_numpy(g["coeff"]).to(cuda)
+    for key, kw in (("diff", {}), ("phase", {"return_phase": True}), ("both", {"return_both": True})):
+        got = spp.extract_phase(coeff, **kw).cpu()
+        ref = torch.from_numpy(g[key])
+        err = (got - ref).abs().max().item()
+        print("extract_phase %s: max|err| %.2e" % (key, err))
+        assert got.shape == ref.shape and err < PHASE_TOL
+    both = spp.extract_phase(coeff, return_both=True)
+    assert float(both[:, :, coeff.shape[2] - 1:].abs().max()) == 0.0
+    # maps larger than one CTA tile
+    big = torch.randn(1, 2, 4, 64, 64, 2, generator=torch.Generator().manual_seed(6))
+    for kw in ({}, {"return_phase": True}, {"return_both": True}):
+        got = spp.extract_phase(big.to(cuda), **kw).cpu()
+        ref = O.extract_phase(big, **kw)
+        assert got.shape == ref.shape and (got - ref).abs().max().item() < PHASE_TOL

@@ -99,3 +99,44 @@ def test_resnet_structure():
     assert net._modules.get("pool5_7x7_s1") is not None
     f = O.resnet_pool5(O.resnet_synthetic(1), torch.zeros(1, 3, 224, 224))
     assert f.shape == (1, 2048)
+
+
+@pytest.mark.parametrize("name", ["scf_64", "scf_50"])
+def test_full_pyramid_and_reconstruction_match_reference(golden_dir, name):
+    """SCFpyr_PyTorch.build / reconstruct of un-mirrored images: the oracle restatement and the host tables the CUDA
+    path consumes (plan_tables.full_pyramid_tables, evaluated in NumPy) against the unmodified reference's outputs."""
+    from steerable import plan_tables
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    x = torch.from_numpy(g["x"])
+    height, nbands = int(g["height"]), int(g["nbands"])
+    coeff = O.pyramid_build(x, height, nbands)
+    units = plan_tables.full_pyramid_tables(x.shape[-1], height, nbands)
+    emu = plan_tables.emulate_full(units, g["x"][:, 0])
+    assert len(coeff) == len(units) == height
+    for i, c in enumerate(coeff):
+        ref = g["c%d" % i]
+        if isinstance(c, list):
+            assert torch.equal(torch.stack(c, 0), torch.from_numpy(ref))
+            e = np.stack(emu[i])
+            assert np.abs(e.real - ref[..., 0]).max() < 2e-6 and np.abs(e.imag - ref[..., 1]).max() < 2e-6
+        else:
+            assert torch.equal(c, torch.from_numpy(ref))
+            assert np.abs(emu[i] - ref).max() < 2e-6
+    rec = O.pyramid_reconstruct(coeff, nbands)
+    assert (rec - torch.from_numpy(g["rec"])).abs().max() < 1e-6
+    assert (rec - x[:, 0]).abs().max() < 2e-5                       # the reference's own round-trip property (SURVEY section 4)
+    emu_rec = plan_tables.emulate_reconstruct(units, emu, x.shape[-1])
+    assert np.abs(emu_rec - g["rec"]).max() < 1e-5
+
+
+def test_extract_phase_variants_match_reference(golden_dir):
+    """Steerable_Pyramid_Phase.extract_phase (Aff-wild-exps/utils.py:367-432): default / return_phase / return_both."""
+    g = np.load(os.path.join(golden_dir, "extract_phase.npz"))
+    coeff = torch.from_numpy(g["coeff"])
+    assert torch.equal(O.extract_phase(coeff), torch.from_numpy(g["diff"]))
+    assert torch.equal(O.extract(coeff), torch.from_numpy(g["diff"]))          # same tail as the api/ extractor
+    assert torch.equal(O.extract_phase(coeff, return_phase=True), torch.from_numpy(g["phase"]))
+    both = O.extract_phase(coeff, return_both=True)
+    assert torch.equal(both, torch.from_numpy(g["both"]))
+    t = coeff.shape[2]
+    assert both.shape[2] == 2 * (t - 1) and float(both[:, :, t - 1:].abs().max()) == 0.0   # insert_tensors fills only T-1 slots
