@@ -56,6 +56,41 @@ class Resnet50_Extractor(object):
         """Device-resident variant of get_vec: float32 CUDA in, (bs,2048) float32 CUDA out."""
         return self.model.pool5(image)
 
+    def features_host(self, image_host, chunk=128, to_host=True):
+        """get_vec for a HOST batch (pinned for a truly asynchronous copy): (bs,3,224,224) float32 -> (bs,2048).  The
+        images are streamed to the device in chunks on a copy stream, double buffered, while ResNet50 runs on the
+        previous chunk; the features come back in one copy (or stay on the device with to_host=False)."""
+        device = get_device()
+        main = torch.cuda.current_stream(device)
+        if getattr(self, '_copy_stream', None) is None or self._bufs[0].shape[0] != chunk:
+            self._copy_stream = torch.cuda.Stream(device)
+            self._bufs = [torch.empty((chunk, 3, 224, 224), dtype=torch.float32, device=device) for _ in range(2)]
+        copy, bufs = self._copy_stream, self._bufs
+        n = image_host.shape[0]
+        spans = [(s, min(n, s + chunk)) for s in range(0, n, chunk)]
+        ready = [torch.cuda.Event() for _ in spans]
+        free = [torch.cuda.Event() for _ in spans]
+        copy.wait_stream(main)
+
+        def issue(k):
+            s, e = spans[k]
+            with torch.cuda.stream(copy):
+                if k >= 2:
+                    copy.wait_event(free[k - 2])
+                bufs[k % 2][:e - s].copy_(image_host[s:e], non_blocking=True)
+                ready[k].record(copy)
+
+        feats = torch.empty((n, 2048), dtype=torch.float32, device=device)
+        for k in range(min(2, len(spans))):
+            issue(k)
+        for k, (s, e) in enumerate(spans):
+            main.wait_event(ready[k])
+            feats[s:e] = self.features(bufs[k % 2][:e - s])
+            free[k].record(main)
+            if k + 2 < len(spans):
+                issue(k + 2)
+        return feats.cpu() if to_host else feats
+
     def features_from_crops(self, crops, preprocessor):
         """(bs,S,S,3) uint8 CUDA face crops -> (bs,2048) float32 CUDA: `self.transform` (Resize 256 ->
         CenterCrop 224 -> ToTensor -> x255 -> Normalize) runs on the device, bit-exact with PIL."""

@@ -43,4 +43,25 @@ inline int upload(T** dev, const T* host, size_t count) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+
+// One-time setup that CUDA keeps PER DEVICE (cudaFuncSetAttribute, __constant__ tables, occupancy queries): a bit per
+// device ordinal instead of a process-wide flag, so a second GPU used by the same process is set up as well.
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  bool need() const { return !(done.load(std::memory_order_acquire) & (1ull << (current_device() & 63))); }
+  void mark() { done.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
+
+// Handles own device memory allocated on the device that was current at create time; calls must come with that
+// device current (the Python layer creates handles per device).
+#define MM_CHECK_DEVICE(owner)                                                                        \
+  do {                                                                                                \
+    const int _cur = ::mimamo::current_device();                                                      \
+    if (_cur != (owner)) {                                                                            \
+      ::mimamo::set_error("this handle lives on CUDA device %d but device %d is current", (owner), _cur); \
+      return MIMAMO_E_VALUE;                                                                          \
+    }                                                                                                 \
+  } while (0)
+
 }  // namespace mimamo

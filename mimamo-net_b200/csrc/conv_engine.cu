@@ -1293,11 +1293,12 @@ static uint32_t make_idesc2(int block_n, ElemType elem) {    // cta_group::2: M 
 int out_size(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
 static int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  const int dev = current_device();
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -1311,10 +1312,10 @@ static double g_prof_flops = 0.0;
 template <int BLOCK_N, bool BF16, bool HAS_RES>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -1333,8 +1334,12 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   }
   if (p.pair) {
     cudaLaunchConfig_t cfg = {};
-    static int max_pairs = 0;
-    if (!max_pairs) max_pairs = max_pairs_for(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, Cfg::kSmemBytes);
+    static std::atomic<int> pairs_cache[64];
+    int max_pairs = pairs_cache[current_device() & 63].load(std::memory_order_relaxed);
+    if (!max_pairs) {
+      max_pairs = max_pairs_for(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, Cfg::kSmemBytes);
+      pairs_cache[current_device() & 63].store(max_pairs, std::memory_order_relaxed);
+    }
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);   // whole, co-resident clusters only
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
@@ -1376,10 +1381,10 @@ static int max_pairs_for(Kernel kernel, size_t smem_bytes) {
 template <bool BF16, bool HAS_RES>
 static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<256, HAS_RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     MM_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<256, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_profile) {
@@ -1396,8 +1401,12 @@ static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   }
   cudaLaunchConfig_t cfg = {};
   const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-  static int max_pairs = 0;
-  if (!max_pairs) max_pairs = max_pairs_for(conv_gemm2_kernel<256, BF16, HAS_RES>, Cfg::kSmemBytes);
+  static std::atomic<int> pairs_cache[64];
+  int max_pairs = pairs_cache[current_device() & 63].load(std::memory_order_relaxed);
+  if (!max_pairs) {
+    max_pairs = max_pairs_for(conv_gemm2_kernel<256, BF16, HAS_RES>, Cfg::kSmemBytes);
+    pairs_cache[current_device() & 63].store(max_pairs, std::memory_order_relaxed);
+  }
   cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -1421,11 +1430,8 @@ static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& 
 // BLOCK_N actually launched: residual layers use at most 128 columns (the residual ring takes the
 // shared memory of two 256-wide pipeline stages).
 static int effective_block_n(const ConvLayer& L, bool has_res) {
-  static int res_bn = 0;
-  if (!res_bn) {
-    const char* e = getenv("MIMAMO_RES_BLOCK_N");
-    res_bn = (e && atoi(e) == 128) ? 128 : 256;      // 256: each tile writes whole 512-byte pixel rows (measured 33.3 -> 32.4 ms per 2048 images)
-  }
+  const char* e = getenv("MIMAMO_RES_BLOCK_N");        // read per call: the switches below are experiment / test knobs, never cached
+  const int res_bn = (e && atoi(e) == 128) ? 128 : 256;      // 256: each tile writes whole 512-byte pixel rows (measured 33.3 -> 32.4 ms per 2048 images)
   return (has_res && L.block_n > res_bn) ? res_bn : L.block_n;
 }
 
@@ -1450,14 +1456,12 @@ static int out_map_spatial(CUtensorMap* map, ElemType elem, void* out, int ldc, 
 
 // MIMAMO_STORE_MODE = "<flat><strided 1x1><3x3>" digits (default "012") selects the epilogue store granularity per layer kind
 static int store_mode_setting(int kind) {
-  static int modes[3] = {-1, -1, -1};
-  if (modes[0] < 0) {
-    const char* e = getenv("MIMAMO_STORE_MODE");
-    const char* d = (e && strlen(e) == 3) ? e : "012";
-    for (int i = 0; i < 3; ++i) modes[i] = (d[i] >= '0' && d[i] <= '2') ? d[i] - '0' : i;
-    if (modes[1] == 0) modes[1] = 1;                          // per-warp boxes only exist for flat layers
-    if (modes[2] == 0) modes[2] = 1;
-  }
+  int modes[3];
+  const char* e = getenv("MIMAMO_STORE_MODE");
+  const char* d = (e && strlen(e) == 3) ? e : "012";
+  for (int i = 0; i < 3; ++i) modes[i] = (d[i] >= '0' && d[i] <= '2') ? d[i] - '0' : i;
+  if (modes[1] == 0) modes[1] = 1;                            // per-warp boxes only exist for flat layers
+  if (modes[2] == 0) modes[2] = 1;
   return modes[kind];
 }
 
@@ -1479,10 +1483,10 @@ static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b
 template <int BLOCK_N, bool BF16>
 static int launch_halo_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
   using Cfg = HaloCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     MM_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BLOCK_N, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -1658,7 +1662,7 @@ static int fill_common(ConvParams& p, const ConvLayer& L, void* out, int ldc, co
   p.idesc = make_idesc(bn, L.elem);
   p.scale = L.scale_dev; p.shift = L.shift_dev;
   p.residual = residual; p.out = out; p.ldc = ldc; p.ld_res = ld_res; p.relu = L.relu;
-  { static int d = -1; if (d < 0) { const char* e = getenv("MIMAMO_DEBUG"); d = e ? atoi(e) : 0; } p.debug = d; }
+  { const char* e = getenv("MIMAMO_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.n_tiles = L.Cout / bn;
   p.cin_blocks = L.Cin_p / kBlockK;
   p.taps_w = L.ksize;
@@ -1821,14 +1825,14 @@ int conv1_s2d_forward(const ConvLayer& L, const void* s2d, int B, void* out, int
   p.a_ptr = s2d;
   p.m_tiles = Ho * B; p.n_tiles = 1;
   p.num_k_blocks = 4;                                        // K = 256 for the flop accounting
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   const bool bf = L.elem == kBF16;
-  if (!attr_set) {
+  if (attr_set.need()) {
     MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
     MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
     MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
     MM_CUDA(cudaFuncSetAttribute(conv1_line_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLineSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   const int units = pool ? B * kPoolBands : p.m_tiles;
   const int grid = units < num_sms() ? units : num_sms();

@@ -36,6 +36,7 @@ struct mimamo_phasenet { PhaseNetPart p; };
 
 struct mimamo_head {
   int num_phase = 12;
+  int device = 0;                         // the CUDA device the weights live on
   MlpPart mlp;
   PhaseNetPart pn;
   LinearLayer transform, xproj[2], classifier;
@@ -211,6 +212,7 @@ extern "C" int mimamo_head_create(const mimamo_tensor_desc* tensors, int32_t n_t
   TensorTable T{tensors, n_tensors};
   mimamo_head* h = new mimamo_head();
   h->num_phase = num_phase;
+  h->device = current_device();
   int rc = mlp_init(T, "mlp.mlp.", h->mlp);
   if (!rc) rc = phasenet_init(T, "phasenet.", 2 * num_phase, h->pn);
   if (!rc) rc = make_linear(T, "transform.0", "transform.2", 256, 512, 1, false, h->transform);
@@ -270,6 +272,7 @@ extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, c
   MM_REQUIRE(h && phase_0 && phase_1 && rgb && out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
   const int M = bs * nf;
   if (M == 0) return MIMAMO_OK;
+  MM_CHECK_DEVICE(h->device);
   cudaStream_t s = (cudaStream_t)stream_;
   const HeadLayout L = head_layout(h, M);
   MM_REQUIRE(workspace && workspace_bytes >= L.total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", L.total);

@@ -519,10 +519,10 @@ gru_kernel(const float* __restrict__ xproj, const float* __restrict__ whhT, cons
 int gru_layer(const float* xproj, const float* whhT, const float* bhh, int S, int Bt, int Hd, float* y, cudaStream_t s) {
   MM_REQUIRE(Hd == kGruHd, MIMAMO_E_RUNTIME, "GRU kernel is specialised for hidden size 128");
   if (S == 0 || Bt == 0) return MIMAMO_OK;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr;
+  if (attr.need()) {
     MM_CUDA(cudaFuncSetAttribute(gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGruSmem));
-    attr = true;
+    attr.mark();
   }
   dim3 grid((Bt + kGruRows - 1) / kGruRows, 2);
   gru_kernel<<<grid, kGruG, kGruSmem, s>>>(xproj, whhT, bhh, S, Bt, y);

@@ -304,14 +304,14 @@ static size_t tail_smem(const TailGeom& g) {
          2 * (size_t)g.trp * g.tcp * sizeof(float);
 }
 
-static bool g_tail_ready = false;
+static DeviceOnce g_tail_ready;               // the __constant__ taps and the function attribute are per device
 static int tail_setup() {
-  if (g_tail_ready) return MIMAMO_OK;
+  if (!g_tail_ready.need()) return MIMAMO_OK;
   float taps[kTaps];
   for (int d = 0; d < kTaps; ++d) taps[d] = (float)exp(-(double)((d - kHalo) * (d - kHalo)) / 8.0);   // std = 2
   MM_CUDA(cudaMemcpyToSymbol(c_gauss, taps, sizeof(taps)));
   MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-  g_tail_ready = true;
+  g_tail_ready.mark();
   return MIMAMO_OK;
 }
 

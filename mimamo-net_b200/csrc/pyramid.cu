@@ -226,6 +226,7 @@ struct mimamo_pyr_plan {
   size_t smem_bytes;
   int large_grid;       // persistent grid size in large-frame mode
   float* dev_blob;      // one allocation holding every table
+  int device = 0;       // the CUDA device the tables live on
 };
 
 extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t nbands,
@@ -303,11 +304,12 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   plan->large_grid = 2 * sms;
-  static size_t max_smem_set = 0;          // several plans may coexist: only ever raise the limit
+  static std::atomic<size_t> max_smem_set[64];     // per device; several plans may coexist: only ever raise the limit
   cudaError_t e = cudaSuccess;
-  if (plan->smem_bytes > max_smem_set) {
+  plan->device = dev;
+  if (plan->smem_bytes > max_smem_set[dev & 63].load()) {
     e = cudaFuncSetAttribute(pyr_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-    if (e == cudaSuccess) max_smem_set = plan->smem_bytes;
+    if (e == cudaSuccess) max_smem_set[dev & 63].store(plan->smem_bytes);
   }
   if (e != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
     set_error("pyramid plan setup failed: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
@@ -335,6 +337,7 @@ int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n
                      cudaStream_t stream) {
   MM_REQUIRE(plan && frames && coeff_out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(n_windows >= 0 && T >= 1, MIMAMO_E_VALUE, "bad batch geometry");
+  MM_CHECK_DEVICE(plan->device);
   if (n_windows == 0) return MIMAMO_OK;
   MM_REQUIRE(n_windows * T < (1ll << 31), MIMAMO_E_VALUE, "too many frames for one launch");
   OutPtrs outs;

@@ -37,6 +37,7 @@ struct mimamo_resnet50 {
   int calib = 2;                   // MIMAMO_RESNET_CALIB: weight rounding 0 = to nearest, 1 = zero-sum residuals, 2 = mean-compensated against
                                    // channel means measured on a built-in synthetic batch at create time (conv_layer_quantize)
   std::vector<ResBlock> blocks;
+  int device = 0;                  // the CUDA device the weights live on
   int chunk = 2048;                // images per pass: larger chunks amortise per-launch ramp/tail (measured per 2048 images: 128: 41.4 ms, 512: 37.6 ms
                                    // on the first engine; 512: 28.3, 1024: 27.2, 2048: 26.5 ms now); 12 MB of workspace per image
 };
@@ -71,6 +72,7 @@ extern "C" int mimamo_resnet50_create(const mimamo_tensor_desc* tensors, int32_t
   MM_REQUIRE(tensors && net_out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
   TensorTable T{tensors, n_tensors};
   mimamo_resnet50* net = new mimamo_resnet50();
+  net->device = current_device();
   const char* dt = getenv("MIMAMO_RESNET_DTYPE");
   net->elem = (dt && strcmp(dt, "bf16") == 0) ? kBF16 : kF16;
   const char* ck = getenv("MIMAMO_RESNET_CHUNK");
@@ -168,6 +170,7 @@ static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mi
   size_t need = 0;
   mimamo_resnet50_workspace_bytes(net, batch, &need);
   MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
+  MM_CHECK_DEVICE(net->device);
   const int chunk = batch < net->chunk ? batch : net->chunk;
   uint16_t* base = reinterpret_cast<uint16_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   uint16_t* A0 = base;

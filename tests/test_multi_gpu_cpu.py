@@ -26,6 +26,9 @@ def _worker(rank, world, port, lengths, q):
     for v, p in enumerate(everything):
         want = torch.arange(lengths[v] * 2, dtype=torch.float32).view(lengths[v], 2) + 1000 * v
         ok = ok and p.shape == want.shape and torch.equal(p, want)
+    # gather to one rank only (bench.py / run_videos(dst=0)): rank 0 gets everything as host tensors, rank 1 nothing
+    on_zero = gather_predictions(local, len(lengths), dst=0, to_host=True)
+    ok = ok and ((on_zero is None) if rank != 0 else all(torch.equal(a, b) for a, b in zip(on_zero, everything)))
     q.put((rank, ok, (lo, hi)))
     dist.destroy_process_group()
 
