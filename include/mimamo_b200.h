@@ -55,7 +55,7 @@ typedef struct mimamo_pyr_plan mimamo_pyr_plan;
 typedef struct {
   int32_t c;                 /* kept crop: outputs y,x in [0,c)                              */
   int32_t h;                 /* folded frequency count                                        */
-  int32_t hp, cp;            /* h, c padded to multiples of 4 (leading dimensions)            */
+  int32_t hp, cp;            /* h, c padded to multiples of 8 (leading dimensions)            */
   const float*   trig_host;  /* [2][hp][cp]  cos/sin(pi k/S + 2 pi k y/s)                     */
   const float*   masks_host; /* [nbands][2 ch][2 half][hp][hp], transposed ([l][k])           */
   const int32_t* inner_sel_host; /* [2 ch][2 half]: 0 = cos table, 1 = sin table              */

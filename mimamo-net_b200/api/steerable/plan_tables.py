@@ -34,7 +34,8 @@ import numpy as np
 
 
 def _pad4(n: int) -> int:
-    return (n + 3) // 4 * 4
+    """Leading dimensions are padded to multiples of 8 (the kernel's 4x8 / 8x4 register tiles need no edge handling)."""
+    return (n + 7) // 8 * 8
 
 
 # ---- the reference's mask recipe (host, float64) -------------------------------------------
@@ -110,8 +111,8 @@ class LevelTables:
     s: int                     # transform size of this level (extended domain)
     c: int                     # kept crop: outputs y, x in [0, c)
     h: int                     # folded frequency count (k, l in [0, h))
-    hp: int                    # h padded to a multiple of 4
-    cp: int                    # c padded to a multiple of 4
+    hp: int                    # h padded to a multiple of 8
+    cp: int                    # c padded to a multiple of 8
     trig: np.ndarray           # float32 [2][hp][cp]: cos / sin of pi k / S + 2 pi k y / s
     masks: np.ndarray          # float32 [nb][2 ch][2 half][hp (l)][hp (k)]  (transposed: [l][k])
     inner_sel: np.ndarray      # int32  [2 ch][2 half]: 0 -> cos table, 1 -> sin table for b_l(x)

@@ -145,7 +145,7 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
       for (int u = 0; u < 4; ++u) {
         const int c = cell[u];
         if (c < 0) continue;
-        // polar: the fused paths converted each distinct frame to (phase, magnitude) once (coeff_to_polar_kernel),
+        // polar: the fused paths store each distinct frame's coefficients as (phase, magnitude) (pyr_build_kernel's epilogue),
         // so the 13 windows sharing a frame do not repeat the atan2 / sqrt
         const float ph = polar ? v[u].x : atan2f(v[u].y, v[u].x);
         const float mag = polar ? v[u].y : __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].x, v[u].x))), 1e-10f);
@@ -346,36 +346,6 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   return MIMAMO_OK;
 }
 
-// (re, im) -> (atan2(im, re), sqrt(re^2 + im^2) + 1e-10) in place, once per DISTINCT frame -- the same fp32 operations
-// the tail would otherwise repeat for each of the 13 windows a frame belongs to (bit-identical results).
-// frames whose root is another frame (window-batch path) hold no coefficients and are skipped.
-__global__ void __launch_bounds__(256)
-coeff_to_polar_kernel(float2* __restrict__ coeff, long long n_frames, int T, int nb, long long plane, const int* __restrict__ root) {
-  const long long f = blockIdx.x;
-  if (root != nullptr && root[f] != (int)f) return;
-  const long long w = f / T;
-  const int t = (int)(f - w * T);
-  for (int b = 0; b < nb; ++b) {
-    float2* p = coeff + (((size_t)w * nb + b) * T + t) * plane;
-    for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.y * blockDim.x) {
-      const float2 v = p[i];
-      float2 o;
-      o.x = atan2f(v.y, v.x);
-      o.y = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
-      p[i] = o;
-    }
-  }
-}
-
-int coeff_to_polar_launch(float* coeff, long long n_frames, int T, int nb, int rows, int cols, const int* root, cudaStream_t stream) {
-  if (n_frames == 0) return MIMAMO_OK;
-  const long long plane = (long long)rows * cols;
-  dim3 grid((unsigned)n_frames, (unsigned)((plane + 1023) / 1024 > 8 ? 8 : (plane + 1023) / 1024));
-  coeff_to_polar_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float2*>(coeff), n_frames, T, nb, plane, root);
-  MM_LAUNCH_OK();
-  return MIMAMO_OK;
-}
-
 }  // namespace mimamo
 
 using namespace mimamo;
@@ -445,7 +415,7 @@ __global__ void frame_root_kernel(const int* __restrict__ parent, int n, int* __
 extern "C" int mimamo_pyr_plan_levels(const mimamo_pyr_plan* plan, int32_t* n_levels, int32_t* nbands, int32_t* crops);
 
 int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
-                     float* const* coeff_out, const int* root, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                     float* const* coeff_out, const int* root, void* workspace, size_t workspace_bytes, cudaStream_t stream, int polar);
 extern "C" int mimamo_pyr_build_workspace_bytes(const mimamo_pyr_plan* plan, int64_t n_windows, int32_t T, size_t* bytes_out);
 
 static bool dedup_enabled() {
@@ -506,12 +476,11 @@ extern "C" int mimamo_pyr_phase(const mimamo_pyr_plan* plan, const float* frames
     MM_LAUNCH_OK();
   }
   const size_t idx2 = 2 * align_up((size_t)n_frames * sizeof(int), 256);
-  int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, (char*)workspace + toff, total - toff - idx2, st);
+  // the pyramid kernel leaves (phase, magnitude) pairs: every coefficient is converted once, when it is produced
+  const int polar = 1;
+  int rc = pyr_build_launch(plan, frames, n_windows, T, cptr, root, (char*)workspace + toff, total - toff - idx2, st, polar);
   if (rc) return rc;
-  const int polar = root != nullptr ? 1 : 0;                // with de-duplication every frame is read through root[]
   for (int i = 0; i < nl; ++i) {
-    if (polar) rc = coeff_to_polar_launch(cptr[i], n_frames, T, nb, crops[i], crops[i], root, st);
-    if (rc) return rc;
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
                               workspace_bytes - toff - 2 * align_up((size_t)n_frames * sizeof(int), 256), st, root, nb, 0, polar);
     if (rc) return rc;
@@ -565,11 +534,9 @@ extern "C" int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float
   float* cptr[MIMAMO_MAX_LEVELS];
   for (int i = 0; i < nl; ++i) cptr[i] = reinterpret_cast<float*>((char*)workspace + coff[i]);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = pyr_build_launch(plan, frames, n_frames, 1, cptr, nullptr, (char*)workspace + toff, total - toff, st);
+  int rc = pyr_build_launch(plan, frames, n_frames, 1, cptr, nullptr, (char*)workspace + toff, total - toff, st, 1);
   if (rc) return rc;
   for (int i = 0; i < nl; ++i) {
-    rc = coeff_to_polar_launch(cptr[i], n_frames, 1, nb, crops[i], crops[i], nullptr, st);
-    if (rc) return rc;
     rc = phase_extract_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out[i], (char*)workspace + toff,
                               total - toff, st, window_index, nb, 1, 1);
     if (rc) return rc;

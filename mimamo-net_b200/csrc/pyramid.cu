@@ -24,7 +24,7 @@ struct LevelDev {
   const float* trig;    // [2][hp][cp]
   const float* masks;   // [nb][2][2][hp][hp]
   int inner_sel[2][2];
-  int units_per_chunk;  // how many (band,ch) units fit the work region at once
+  int units_per_chunk;  // how many bands (4 * hp * cp floats each) fit the work region at once
 };
 
 struct PlanDev {
@@ -43,39 +43,52 @@ __device__ __forceinline__ float4 ld4(const float* p, bool global) {
   return global ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
 }
 
-// acc[r][c] += sum_k A[k*lda + r] * (mask) * B[k*ldb + c],  r,c in [0,4)
-template <bool A_GLOBAL, bool B_GLOBAL, bool MASKED>
-__device__ __forceinline__ void tile4x4(const float* __restrict__ A, int lda,
-                                        const float* __restrict__ Mk, int ldm,
-                                        const float* __restrict__ B, int ldb, int K, float (&acc)[4][4]) {
-#pragma unroll 4
+// Register-tiled product of K-major operands:  acc[r][c] += sum_k A[k*lda + r] * (mask[k*ldm + r]) * B[k*ldb + c],
+// r in [0,TM), c in [0,TN).  The first version used 4x4 tiles: two or three 16-byte loads per 16 FMAs kept the kernel on
+// the load/store pipe (~13 % of the fp32 peak at every frame size); 4x8 / 8x4 tiles halve the loads per FMA, and the
+// outer product below shares its table operand between the real and the imaginary channel.
+template <int TM, int TN, bool A_GLOBAL, bool B_GLOBAL, bool MASKED>
+__device__ __forceinline__ void tile_mma(const float* __restrict__ A, int lda, const float* __restrict__ Mk, int ldm,
+                                         const float* __restrict__ B, int ldb, int K, float (&acc)[TM][TN]) {
+#pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    float4 a = ld4(A + (size_t)k * lda, A_GLOBAL);
-    if (MASKED) {
-      const float4 m = __ldg(reinterpret_cast<const float4*>(Mk + (size_t)k * ldm));
-      a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
+    float av[TM], bv[TN];
+#pragma unroll
+    for (int q = 0; q < TM / 4; ++q) {
+      float4 a = ld4(A + (size_t)k * lda + 4 * q, A_GLOBAL);
+      if (MASKED) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(Mk + (size_t)k * ldm + 4 * q));
+        a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
+      }
+      av[4 * q] = a.x; av[4 * q + 1] = a.y; av[4 * q + 2] = a.z; av[4 * q + 3] = a.w;
     }
-    const float4 b = ld4(B + (size_t)k * ldb, B_GLOBAL);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int q = 0; q < TN / 4; ++q) {
+      const float4 b = ld4(B + (size_t)k * ldb + 4 * q, B_GLOBAL);
+      bv[4 * q] = b.x; bv[4 * q + 1] = b.y; bv[4 * q + 2] = b.z; bv[4 * q + 3] = b.w;
+    }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+      for (int c = 0; c < TN; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
   }
 }
 
-__device__ __forceinline__ void zero(float (&acc)[4][4]) {
+template <int TM, int TN>
+__device__ __forceinline__ void zero(float (&acc)[TM][TN]) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int r = 0; r < TM; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < TN; ++c) acc[r][c] = 0.f;
 }
 
-__device__ __forceinline__ void store_rows(float* dst, int ld, const float (&acc)[4][4]) {
+template <int TM, int TN>
+__device__ __forceinline__ void store_rows(float* dst, int ld, const float (&acc)[TM][TN]) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-    *reinterpret_cast<float4*>(dst + (size_t)r * ld) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int q = 0; q < TN / 4; ++q)
+      *reinterpret_cast<float4*>(dst + (size_t)r * ld + 4 * q) = make_float4(acc[r][4 * q], acc[r][4 * q + 1], acc[r][4 * q + 2], acc[r][4 * q + 3]);
 }
 
 __device__ float block_sum(float v, float* scratch) {
@@ -89,7 +102,8 @@ __device__ float block_sum(float v, float* scratch) {
   return tot;
 }
 
-// Forward half: frame -> Ct (kept in shared memory).  Xs / R1 live in the work region.
+// Forward half: frame -> Ct (kept in shared memory).  Xs / R1 live in the work region.  All leading dimensions are
+// multiples of 8 (plan_tables pads), so 4x8 tiles need no edge handling.
 __device__ void frame_spectrum(const PlanDev& P, const float* __restrict__ frame, float* Ct, float* W,
                                float* red) {
   const int H = P.H, Hp = P.Hp, Kp = P.Kp;
@@ -113,69 +127,86 @@ __device__ void frame_spectrum(const PlanDev& P, const float* __restrict__ frame
   __syncthreads();
   // R1[n][k] = sum_m X[m][n] dct[m][k]
   {
-    const int tn = Kp >> 2, tiles = (Hp >> 2) * tn;
+    const int tn = Kp >> 3, tiles = (Hp >> 2) * tn;
     for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-      const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
-      float acc[4][4];
+      const int i0 = (t / tn) << 2, j0 = (t % tn) << 3;
+      float acc[4][8];
       zero(acc);
-      tile4x4<false, true, false>(Xs + i0, Hp, nullptr, 0, P.dct_t + j0, Kp, Hp, acc);
+      tile_mma<4, 8, false, true, false>(Xs + i0, Hp, nullptr, 0, P.dct_t + j0, Kp, Hp, acc);
       store_rows(R1 + (size_t)i0 * Kp + j0, Kp, acc);
     }
   }
   __syncthreads();
   // Ct[l][k] = sum_n dct[n][l] R1[n][k]
   {
-    const int tn = Kp >> 2, tiles = tn * tn;
+    const int tn = Kp >> 3, tiles = (Kp >> 2) * tn;
     for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-      const int i0 = (t / tn) << 2, j0 = (t % tn) << 2;
-      float acc[4][4];
+      const int i0 = (t / tn) << 2, j0 = (t % tn) << 3;
+      float acc[4][8];
       zero(acc);
-      tile4x4<true, false, false>(P.dct_t + i0, Kp, nullptr, 0, R1 + j0, Kp, Hp, acc);
+      tile_mma<4, 8, true, false, false>(P.dct_t + i0, Kp, nullptr, 0, R1 + j0, Kp, Hp, acc);
       store_rows(Ct + (size_t)i0 * Kp + j0, Kp, acc);
     }
   }
   __syncthreads();
 }
 
-// Inner products of one chunk of (band,ch) units: U_u[half*hp + k][x].
-__device__ void band_inner(const PlanDev& P, const LevelDev& L, const float* Ct, float* W, int unit0,
-                           int n_units) {
+// Inner products of one chunk of bands: U[(b*2+ch)*2*hp + half*hp + k][x]  (both channels, both halves of every band).
+__device__ void band_inner(const PlanDev& P, const LevelDev& L, const float* Ct, float* W, int band0, int n_bands) {
   const int hp = L.hp, cp = L.cp;
-  const int tk = hp >> 2, tx = cp >> 2;
-  const int per_job = tk * tx, tiles = n_units * 2 * per_job;
+  const int tk = hp >> 2, tx = cp >> 3;
+  const int per_job = tk * tx, tiles = n_bands * 4 * per_job;
   for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
     const int job = t / per_job, r = t - job * per_job;
-    const int u = job >> 1, half = job & 1;
-    const int unit = unit0 + u, b = unit >> 1, ch = unit & 1;
-    const int i0 = (r / tx) << 2, j0 = (r % tx) << 2;       // i: k, j: x
+    const int u = job >> 1, half = job & 1;                 // u = local (band, ch)
+    const int unit = band0 * 2 + u, b = unit >> 1, ch = unit & 1;
+    const int i0 = (r / tx) << 2, j0 = (r % tx) << 3;       // i: k, j: x
     const float* mask = L.masks + ((size_t)((b * 2 + ch) * 2 + half) * hp) * hp;
     const float* tab = L.trig + (size_t)L.inner_sel[ch][half] * hp * cp;
-    float acc[4][4];
+    float acc[4][8];
     zero(acc);
-    tile4x4<false, true, true>(Ct + i0, P.Kp, mask + i0, hp, tab + j0, cp, hp, acc);
+    tile_mma<4, 8, false, true, true>(Ct + i0, P.Kp, mask + i0, hp, tab + j0, cp, hp, acc);
     store_rows(W + ((size_t)u * 2 * hp + half * hp + i0) * cp + j0, cp, acc);
   }
 }
 
+// Outer products: out_ch[y][x] = sum_kk trig[kk][y] * U_ch[kk][x]; one thread owns an 8 (y) x 4 (x) tile of BOTH channels
+// of a band (the table operand is shared), so the coefficient leaves as (re, im) -- or (phase, magnitude) -- pairs.
 template <class Sink>
-__device__ void band_outer(const LevelDev& L, const float* W, int unit0, int n_units, Sink sink) {
+__device__ void band_outer(const LevelDev& L, const float* W, int band0, int n_bands, Sink sink) {
   const int hp = L.hp, cp = L.cp;
-  const int ty = cp >> 2;
-  const int per_job = ty * ty, tiles = n_units * per_job;
+  const int ty = cp >> 3, tx = cp >> 2;
+  const int per_job = ty * tx, tiles = n_bands * per_job;
   for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
     const int u = t / per_job, r = t - u * per_job;
-    const int i0 = (r / ty) << 2, j0 = (r % ty) << 2;       // i: y, j: x
-    float acc[4][4];
-    zero(acc);
-    tile4x4<true, false, false>(L.trig + i0, cp, nullptr, 0, W + (size_t)u * 2 * hp * cp + j0, cp, 2 * hp, acc);
-    sink(unit0 + u, i0, j0, acc);
+    const int i0 = (r / tx) << 3, j0 = (r % tx) << 2;       // i: y, j: x
+    float re[8][4], im[8][4];
+    zero(re);
+    zero(im);
+    const float* A = L.trig + i0;
+    const float* Bre = W + (size_t)(2 * u) * 2 * hp * cp + j0;
+    const float* Bim = Bre + (size_t)2 * hp * cp;
+#pragma unroll 2
+    for (int k = 0; k < 2 * hp; ++k) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(A + (size_t)k * cp));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(A + (size_t)k * cp + 4));
+      const float4 br = *reinterpret_cast<const float4*>(Bre + (size_t)k * cp);
+      const float4 bi = *reinterpret_cast<const float4*>(Bim + (size_t)k * cp);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float rv[4] = {br.x, br.y, br.z, br.w}, iv[4] = {bi.x, bi.y, bi.z, bi.w};
+#pragma unroll
+      for (int y = 0; y < 8; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { re[y][x] = fmaf(av[y], rv[x], re[y][x]); im[y][x] = fmaf(av[y], iv[x], im[y][x]); }
+    }
+    sink(band0 + u, i0, j0, re, im);
   }
 }
 
 template <bool LARGE>
 __global__ void __launch_bounds__(kPyrThreads)
 pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T,
-                 const __grid_constant__ OutPtrs outs, const int* __restrict__ root, float* scratch, long long n_frames) {
+                 const __grid_constant__ OutPtrs outs, const int* __restrict__ root, float* scratch, long long n_frames, int polar) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
   // Small frames: one CTA per frame, everything in shared memory.  Large frames (H > ~128, e.g. the
@@ -190,24 +221,31 @@ pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ fr
     frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
     for (int li = 0; li < P.n_levels; ++li) {
       const LevelDev& L = P.lv[li];
-      const int total = P.nb * 2;
-      float* out = outs.p[li];
+      float2* out = reinterpret_cast<float2*>(outs.p[li]);
       const int c = L.c;
-      for (int unit0 = 0; unit0 < total; unit0 += L.units_per_chunk) {
-        const int n_units = min(L.units_per_chunk, total - unit0);
-        band_inner(P, L, Ct, W, unit0, n_units);
+      for (int band0 = 0; band0 < P.nb; band0 += L.units_per_chunk) {
+        const int n_bands = min(L.units_per_chunk, P.nb - band0);
+        band_inner(P, L, Ct, W, band0, n_bands);
         __syncthreads();
-        band_outer(L, W, unit0, n_units, [&](int unit, int y0, int x0, const float (&acc)[4][4]) {
-          const int b = unit >> 1, ch = unit & 1;
-          float* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c * 2 + ch;
+        band_outer(L, W, band0, n_bands, [&](int b, int y0, int x0, const float (&re)[8][4], const float (&im)[8][4]) {
+          float2* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
+          for (int r = 0; r < 8; ++r) {
             const int y = y0 + r;
             if (y >= c) continue;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int x = x0 + q;
-              if (x < c) base[((size_t)y * c + x) * 2] = acc[r][q];
+              if (x >= c) continue;
+              float2 v = make_float2(re[r][q], im[r][q]);
+              if (polar) {
+                // (phase, magnitude) exactly as the phase tail computes them from (re, im): the fused paths store the
+                // polar form once per distinct frame so that the 13 windows sharing it do not repeat the atan2 / sqrt
+                const float ph = atan2f(v.y, v.x);
+                const float mg = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+                v = make_float2(ph, mg);
+              }
+              base[(size_t)y * c + x] = v;
             }
           }
         });
@@ -234,11 +272,11 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
                                       const mimamo_pyr_level_desc* levels, mimamo_pyr_plan** plan_out) {
   MM_REQUIRE(plan_out && dct_t_host && levels, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(n_levels >= 1 && n_levels <= MIMAMO_MAX_LEVELS, MIMAMO_E_VALUE, "n_levels must be in [1,%d]", MIMAMO_MAX_LEVELS);
-  MM_REQUIRE(H >= 1 && Hp % 4 == 0 && Kp % 4 == 0 && Hp >= H && nbands >= 2, MIMAMO_E_VALUE, "bad plan geometry");
+  MM_REQUIRE(H >= 1 && Hp % 8 == 0 && Kp % 8 == 0 && Hp >= H && nbands >= 2, MIMAMO_E_VALUE, "bad plan geometry (leading dimensions must be multiples of 8)");
   size_t total = (size_t)Hp * Kp;
   for (int i = 0; i < n_levels; ++i) {
     const mimamo_pyr_level_desc& L = levels[i];
-    MM_REQUIRE(L.hp % 4 == 0 && L.cp % 4 == 0 && L.hp >= L.h && L.cp >= L.c && L.hp <= Kp, MIMAMO_E_VALUE, "bad level %d geometry", i);
+    MM_REQUIRE(L.hp % 8 == 0 && L.cp % 8 == 0 && L.hp >= L.h && L.cp >= L.c && L.hp <= Kp, MIMAMO_E_VALUE, "bad level %d geometry", i);
     total += (size_t)2 * L.hp * L.cp + (size_t)nbands * 4 * L.hp * L.hp;
   }
   mimamo_pyr_plan* plan = new mimamo_pyr_plan();
@@ -258,7 +296,7 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
   };
   d.dct_t = put(dct_t_host, (size_t)Hp * Kp);
   // shared-memory budget: Ct + a work region that must hold the forward scratch (X + R1) and at
-  // least one (band,ch) unit of every level; larger regions batch more units per barrier.
+  // least one band (both channels, both halves) of every level; larger regions batch more bands per barrier.
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -266,18 +304,18 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
   size_t need = (size_t)Hp * Hp + (size_t)Hp * Kp;
   size_t want = need;
   for (int i = 0; i < n_levels; ++i) {
-    const size_t unit = (size_t)2 * levels[i].hp * levels[i].cp;
+    const size_t unit = (size_t)4 * levels[i].hp * levels[i].cp;
     need = need > unit ? need : unit;
-    const size_t all = unit * 2 * nbands;
+    const size_t all = unit * nbands;
     want = want > all ? want : all;
   }
   const size_t budget_floats = ((size_t)max_optin - 1024) / sizeof(float);
   size_t work;
   d.large = (ct_floats + need > budget_floats) ? 1 : 0;
   if (d.large) {
-    work = need;                       // one (band,ch) unit at a time, buffers in global scratch
+    work = need;                       // one band at a time, buffers in global scratch
   } else {
-    // Work-region size: big enough to batch every (band,ch) unit of a level between barriers if
+    // Work-region size: big enough to batch every band of a level between barriers if
     // that still leaves room for two CTAs per SM; otherwise as large as one CTA may have.
     const size_t half_budget = budget_floats / 2;
     if (ct_floats + want <= half_budget) work = want;
@@ -295,9 +333,9 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
     o.masks = put(L.masks_host, (size_t)nbands * 4 * L.hp * L.hp);
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b) o.inner_sel[a][b] = L.inner_sel_host[a * 2 + b];
-    const size_t unit = (size_t)2 * L.hp * L.cp;
+    const size_t unit = (size_t)4 * L.hp * L.cp;
     int fit = (int)(work / unit);
-    if (fit > 2 * nbands) fit = 2 * nbands;
+    if (fit > nbands) fit = nbands;
     o.units_per_chunk = fit < 1 ? 1 : fit;
   }
   plan->smem_bytes = d.large ? 0 : (ct_floats + work) * sizeof(float);
@@ -334,7 +372,7 @@ static size_t pyr_scratch_bytes(const mimamo_pyr_plan* plan) {
 
 int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows, int32_t T,
                      float* const* coeff_out, const int* root, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int polar) {
   MM_REQUIRE(plan && frames && coeff_out, MIMAMO_E_VALUE, "null argument");
   MM_REQUIRE(n_windows >= 0 && T >= 1, MIMAMO_E_VALUE, "bad batch geometry");
   MM_CHECK_DEVICE(plan->device);
@@ -350,9 +388,9 @@ int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n
     const size_t need = pyr_scratch_bytes(plan);
     MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
     const unsigned grid = (unsigned)(n_frames < plan->large_grid ? n_frames : plan->large_grid);
-    pyr_build_kernel<true><<<grid, kPyrThreads, 0, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames);
+    pyr_build_kernel<true><<<grid, kPyrThreads, 0, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames, polar);
   } else {
-    pyr_build_kernel<false><<<(unsigned)n_frames, kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root, nullptr, n_frames);
+    pyr_build_kernel<false><<<(unsigned)n_frames, kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root, nullptr, n_frames, polar);
   }
   MM_LAUNCH_OK();
   return MIMAMO_OK;
@@ -366,7 +404,7 @@ extern "C" int mimamo_pyr_build_workspace_bytes(const mimamo_pyr_plan* plan, int
 
 extern "C" int mimamo_pyr_build(const mimamo_pyr_plan* plan, const float* frames, int64_t n_windows,
                                 int32_t T, float* const* coeff_out, void* workspace, size_t workspace_bytes, void* stream) {
-  return pyr_build_launch(plan, frames, n_windows, T, coeff_out, nullptr, workspace, workspace_bytes, (cudaStream_t)stream);
+  return pyr_build_launch(plan, frames, n_windows, T, coeff_out, nullptr, workspace, workspace_bytes, (cudaStream_t)stream, 0);
 }
 
 // accessors used by the fused path in phase_tail.cu
