@@ -365,15 +365,16 @@ def bench_e2e(ctx):
         flat = crops_d.view(WINDOWS, 112, 112, 3)
         widx = tester.clip_window_index(CLIPS, FRAMES, dev)
 
-        def pyramid_stage():
-            return pde.phase_difference_indexed(pre.gray(flat), widx)
+        def pyramid_stage():                                    # gray + pyramid + phase tail, as infer_crops runs it
+            return tester._phase_streams(pre.gray(flat), widx)
 
-        p0, p1 = [d.view(CLIPS, FRAMES, -1, d.shape[-2], d.shape[-1]) for d in pyramid_stage()]
-        feats = rn.features_from_crops(flat, pre).view(CLIPS, FRAMES, 2048)
+        streams = pyramid_stage()
+        feats = rn.features_from_crops(flat, pre)
         stages = {"pyramid_phase_ms": stage_ms(pyramid_stage),
                   "resnet50_ms": stage_ms(lambda: rn.features_from_crops(flat, pre)),
-                  "head_ms": stage_ms(lambda: hd([p0, p1], feats))}
-        del p0, p1, feats
+                  "head_ms": stage_ms(lambda: tester._head(streams, slice(0, WINDOWS), feats, CLIPS, FRAMES)),
+                  "phase_route": streams[0]}
+        del streams, feats
     float_inputs = None
     if args.quick:
         e2e_ms = float("nan")

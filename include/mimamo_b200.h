@@ -147,6 +147,16 @@ int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float* frames, i
                              const int32_t* window_index, int64_t n_windows, int32_t T,
                              float* const* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same clip path feeding PhaseNet directly: level i leaves as fp16 channels band*(T-1) + t of the NHWC tensor
+ * out16[i] = f16[n_windows, c_i, c_i, pitch[i]] at channel offset c_off[i] -- the operands mimamo_head_forward_nhwc16
+ * reads -- instead of fp32 NCHW maps that the head would transpose (no reference counterpart: the reference's
+ * nn.Conv2d takes the fp32 tensor of api/tester.py:131-138).  Needs maps up to 56x56 and (T-1) % 4 == 0; pitch and
+ * offsets multiples of 4.  Workspace as mimamo_pyr_phase_indexed_workspace_bytes. */
+int mimamo_pyr_phase_indexed_nhwc16(const mimamo_pyr_plan* plan, const float* frames, int64_t n_frames,
+                                    const int32_t* window_index, int64_t n_windows, int32_t T,
+                                    void* const* out16, const int32_t* pitch, const int32_t* c_off,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Face-crop preprocessing on the device, bit-exact with the
  * reference's PIL / torchvision transforms:
@@ -223,6 +233,14 @@ int  mimamo_head_workspace_bytes(const mimamo_head* head, int32_t bs, int32_t nf
 int  mimamo_head_forward(const mimamo_head* head, const float* phase_0, const float* phase_1,
                          const float* rgb, int32_t bs, int32_t nf, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Head forward fed by mimamo_pyr_phase_indexed_nhwc16: phase0_nhwc f16[bs*nf,48,48,phase0_pitch] (the 2*num_phase level-0
+ * channels; phase0_pitch a multiple of 8), cat_nhwc f16[bs*nf,24,24,128] with the level-1 channels at [64, 64+2*num_phase)
+ * and ZEROS above them (channels [0,64) are scratch: conv_net[0][3] writes its output there, the skip concatenation of
+ * api/mimamo_net.py:85). */
+int  mimamo_head_forward_nhwc16(const mimamo_head* head, const void* phase0_nhwc, int32_t phase0_pitch, void* cat_nhwc,
+                                const float* rgb, int32_t bs, int32_t nf, float* out,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* The two streams of the head on their own: MLP.forward (api/mimamo_net.py:22-26; keys `mlp.{1,2,5,6,...}`, any depth,
  * last width 256) and PhaseNet.forward for 48x48 inputs (:79-95; keys `conv_net.*`, `fc.*`, `classifier.*`).

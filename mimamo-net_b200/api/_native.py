@@ -67,6 +67,8 @@ _SIGNATURES = {
                                                                 ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_pyr_phase_indexed": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.c_int32,
                                                 ctypes.POINTER(vp), vp, ctypes.c_size_t, vp]),
+    "mimamo_pyr_phase_indexed_nhwc16": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.c_int32,
+                                                       ctypes.POINTER(vp), c_int32_p, c_int32_p, vp, ctypes.c_size_t, vp]),
     "mimamo_preproc_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int32_p,
                                              ctypes.c_int32, ctypes.c_int32, c_int32_p, c_int32_p, ctypes.c_int32,
                                              ctypes.c_int32, c_float_p, ctypes.POINTER(vp)]),
@@ -87,6 +89,8 @@ _SIGNATURES = {
                                                    ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_head_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
                                            ctypes.c_size_t, vp]),
+    "mimamo_head_forward_nhwc16": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp,
+                                                  ctypes.c_size_t, vp]),
     "mimamo_mlp_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.POINTER(vp)]),
     "mimamo_mlp_destroy": (None, [vp]),
     "mimamo_mlp_in_features": (ctypes.c_int, [vp]),

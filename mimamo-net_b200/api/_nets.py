@@ -118,6 +118,25 @@ class NativeHead(_Handle):
                                               _native.stream_ptr(rgb.device)))
         return out
 
+    def forward_nhwc16(self, phase0, cat, rgb):
+        """phase0 f16 (bs*nf, 48, 48, C), cat f16 (bs*nf, 24, 24, 128) as Phase_Difference_Extractor.phasenet_operands
+        returns them (cat[..., :64] is overwritten), rgb f32 (bs, nf, 2048) -> (bs, nf, 2)."""
+        bs, nf = rgb.shape[0], rgb.shape[1]
+        c = self.channels
+        assert phase0.is_cuda and phase0.dtype == torch.float16 and tuple(phase0.shape) == (bs * nf, 48, 48, c) and phase0.is_contiguous()
+        assert cat.is_cuda and cat.dtype == torch.float16 and tuple(cat.shape) == (bs * nf, 24, 24, 128) and cat.is_contiguous()
+        assert rgb.is_cuda and rgb.dtype == torch.float32 and rgb.shape[2] == 2048
+        rgb = rgb.contiguous()
+        out = torch.empty((bs, nf, 2), dtype=torch.float32, device=rgb.device)
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_head_workspace_bytes(self.handle, bs, nf, ctypes.byref(need)))
+        ws = self.workspace(need.value, rgb.device)
+        _native.check(lib.mimamo_head_forward_nhwc16(self.handle, _native.dptr(phase0), c, _native.dptr(cat), _native.dptr(rgb),
+                                                     bs, nf, _native.dptr(out), _native.dptr(ws), ws.numel(),
+                                                     _native.stream_ptr(rgb.device)))
+        return out
+
 
 class NativeMLP(_Handle):
     """MLP.forward on its own (mimamo_mlp_*): state_dict keys `mlp.{1,2,5,6,...}`."""

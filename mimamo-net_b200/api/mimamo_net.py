@@ -132,3 +132,13 @@ class Two_Stream_RNN(nn.Module):
         phase_0, phase_1 = phase_data
         with torch.no_grad():
             return self._native.forward(phase_0, phase_1, rgb_data)
+
+    def forward_operands(self, phase0_nhwc, cat_nhwc, rgb_data):
+        """forward() fed by Phase_Difference_Extractor.phasenet_operands (fp16 NHWC phase differences straight from the
+        phase tail); bit-identical to forward() on the fp32 phase tensors."""
+        if self.training:
+            raise RuntimeError('Two_Stream_RNN (B200) is inference only: call .eval() first')
+        if self._native is None:
+            self.refresh()
+        with torch.no_grad():
+            return self._native.forward_nhwc16(phase0_nhwc, cat_nhwc, rgb_data)

@@ -157,6 +157,42 @@ class Phase_Difference_Extractor(object):
                                                    _native.stream_ptr(frames.device)))
         return outs[0] if isinstance(self.extract_level, int) else outs
 
+    def phasenet_operands(self, frames, window_index, out=None):
+        """phase_difference_indexed for the two-level Tester configuration, delivered as the fp16 NHWC operands PhaseNet
+        reads (mimamo_pyr_phase_indexed_nhwc16): (phase0 (n_windows, c0, c0, C) , cat (n_windows, c1, c1, 128)) with
+        C = nbands * (T-1) channels, level 1 sitting at channels [64, 64 + C) of `cat` and zeros above.  Returns None when
+        the configuration has no such path (callers then use phase_difference_indexed + the fp32 head entry).  `out`:
+        optional preallocated (phase0, cat) pair -- `cat` must come zero-initialised (torch.zeros) the first time."""
+        n, W, H = frames.size()
+        n_windows, T = window_index.size()
+        C = self.nbands * (T - 1)
+        levels = self._levels()
+        if len(levels) != 2 or (T - 1) % 4 != 0 or C > 64 or C % 8 != 0 or W != H or n_windows == 0:
+            return None
+        plan, _, _, frames = self._prepare(frames.view(n, 1, W, H), True)
+        if plan.crops[0] > 56 or plan.crops[1] * 2 != plan.crops[0]:
+            return None
+        assert window_index.dtype == torch.int32 and window_index.device == frames.device
+        c0, c1 = plan.crops
+        if out is None:
+            phase0 = torch.empty((n_windows, c0, c0, C), dtype=torch.float16, device=frames.device)
+            cat = torch.zeros((n_windows, c1, c1, 128), dtype=torch.float16, device=frames.device)
+        else:
+            phase0, cat = out
+            assert phase0.is_contiguous() and cat.is_contiguous() and phase0.dtype == cat.dtype == torch.float16
+            assert tuple(phase0.shape) == (n_windows, c0, c0, C) and tuple(cat.shape) == (n_windows, c1, c1, 128)
+        window_index = window_index.contiguous()
+        lib = _native.lib()
+        need = ctypes.c_size_t(0)
+        _native.check(lib.mimamo_pyr_phase_indexed_workspace_bytes(plan.handle, n, n_windows, T, ctypes.byref(need)))
+        ws = torch.empty((max(need.value, 8),), dtype=torch.uint8, device=frames.device)
+        pitch = (ctypes.c_int32 * 2)(C, 128)
+        offs = (ctypes.c_int32 * 2)(0, 64)
+        _native.check(lib.mimamo_pyr_phase_indexed_nhwc16(plan.handle, _native.dptr(frames), n, _native.dptr(window_index),
+                                                          n_windows, T, _native.ptr_array([phase0, cat]), pitch, offs,
+                                                          _native.dptr(ws), ws.numel(), _native.stream_ptr(frames.device)))
+        return phase0, cat
+
     def show_3D_subplots(self, data, title, first_k_frames=None):
         raise NotImplementedError('visualisation is out of scope (the reference method uses undefined '
                                   'plt/cm names, api/phase_difference_extractor.py:136-152)')

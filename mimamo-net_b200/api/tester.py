@@ -64,6 +64,47 @@ class Tester(object):
         self.save_size = save_size
         self._crop_preprocessor = None
         self._window_index = {}
+        self._operand_cache = {}
+
+    # PhaseNet operands straight from the phase tail (fp16 NHWC) when the configuration allows it; MIMAMO_PHASE_FP32=1
+    # forces the reference-shaped fp32 phase tensors instead (cross-check: both routes give the same bits).
+    def _operand_buffers(self, n_windows, device):
+        pde = self.phase_difference_extractor
+        if os.environ.get('MIMAMO_PHASE_FP32') == '1' or not isinstance(pde.extract_level, list) or len(pde.extract_level) != 2:
+            return None
+        channels = pde.nbands * self.num_phase
+        if self.num_phase % 4 != 0 or channels % 8 != 0 or channels > 64 or channels != 2 * self.num_phase or self.phase_size != 48:
+            return None
+        key = (n_windows, str(device))
+        if key not in self._operand_cache:
+            if len(self._operand_cache) > 8:
+                self._operand_cache.clear()
+            c = self.phase_size
+            self._operand_cache[key] = (torch.empty((n_windows, c, c, channels), dtype=torch.float16, device=device),
+                                        torch.zeros((n_windows, c // 2, c // 2, 128), dtype=torch.float16, device=device))
+        return self._operand_cache[key]
+
+    def _phase_streams(self, gray, idx):
+        """('operands', phase0_nhwc, cat_nhwc) or ('fp32', phase_0, phase_1), each with one row per window."""
+        bufs = self._operand_buffers(idx.shape[0], gray.device)
+        if bufs is not None:
+            ops = self.phase_difference_extractor.phasenet_operands(gray, idx, out=bufs)
+            if ops is not None:
+                return ('operands',) + tuple(ops)
+        diffs = self.phase_difference_extractor.phase_difference_indexed(gray, idx)
+        return ('fp32',) + tuple(d.view(idx.shape[0], -1, d.shape[-2], d.shape[-1]) for d in diffs)
+
+    def _head(self, streams, rows, feats, b, f):
+        """Head forward over windows `rows` (a slice, or an index tensor) of the phase streams, as b snippets of f frames."""
+        kind, s0, s1 = streams
+        if isinstance(rows, slice):
+            s0, s1, feats = s0[rows], s1[rows], feats[rows]
+        else:
+            s0, s1, feats = s0.index_select(0, rows), s1.index_select(0, rows), feats.index_select(0, rows)
+        feats = feats.reshape(b, f, -1)
+        if kind == 'operands':
+            return self.model.forward_operands(s0, s1, feats)
+        return self.model([s0.reshape(b, f, *s0.shape[1:]), s1.reshape(b, f, *s1.shape[1:])], feats)
 
     # ------------------------------------------------------------------ reference surface
     def test(self, input_video, fast=True):
@@ -215,10 +256,9 @@ class Tester(object):
             flat = crops.reshape(b * f, crops.shape[2], crops.shape[3], crops.shape[4])
             gray = pre.gray(flat)                                                       # (B*F, 48, 48)
             idx = self.clip_window_index(b, f, crops.device)
-            diffs = self.phase_difference_extractor.phase_difference_indexed(gray, idx)
-            phase_0, phase_1 = [d.view(b, f, -1, d.shape[-2], d.shape[-1]) for d in diffs]
-            feats = self.resnet50_extractor.features_from_crops(flat, pre).view(b, f, 2048)
-            return self.model([phase_0, phase_1], feats)
+            streams = self._phase_streams(gray, idx)
+            feats = self.resnet50_extractor.features_from_crops(flat, pre)
+            return self._head(streams, slice(0, b * f), feats, b, f)
 
     def infer_crops_host(self, crops, to_host=True, parts=4):
         """infer_crops from a HOST uint8 tensor (pinned for an asynchronous copy): 37.6 KB per frame cross
@@ -246,6 +286,8 @@ class Tester(object):
                     landed.append(ev)
             dev.record_stream(copy)
             pre = self.crop_preprocessor()
+            pde = self.phase_difference_extractor
+            bufs = self._operand_buffers(b * f, device)
             phase = None
             for k in range(parts):
                 lo, hi = bounds[k], bounds[k + 1]
@@ -254,14 +296,20 @@ class Tester(object):
                 main.wait_event(landed[k])
                 flat = dev[lo:hi].reshape((hi - lo) * f, dev.shape[2], dev.shape[3], dev.shape[4])
                 idx = self.clip_window_index(hi - lo, f, device)
+                if bufs is not None and pde.phasenet_operands(pre.gray(flat), idx, out=(bufs[0][lo * f:hi * f], bufs[1][lo * f:hi * f])) is not None:
+                    continue
+                bufs = None                                                   # configuration without the fp16 operand path
                 if phase is None:
-                    nb, T = self.phase_difference_extractor.nbands, self.num_phase + 1
+                    nb, T = pde.nbands, self.num_phase + 1
                     sizes = [self.phase_size, self.phase_size // 2]
                     phase = [torch.empty((b, f, nb * (T - 1), c, c), dtype=torch.float32, device=device) for c in sizes]
-                self.phase_difference_extractor.phase_difference_indexed(pre.gray(flat), idx, out=[p[lo:hi] for p in phase])
+                pde.phase_difference_indexed(pre.gray(flat), idx, out=[p[lo:hi] for p in phase])
             flat = dev.reshape(b * f, dev.shape[2], dev.shape[3], dev.shape[4])
-            feats = self.resnet50_extractor.features_from_crops(flat, pre).view(b, f, 2048)
-            out = self.model([phase[0], phase[1]], feats)
+            feats = self.resnet50_extractor.features_from_crops(flat, pre)
+            if bufs is not None:
+                out = self.model.forward_operands(bufs[0], bufs[1], feats.view(b, f, 2048))
+            else:
+                out = self.model([phase[0], phase[1]], feats.view(b, f, 2048))
         return out.cpu() if to_host else out
 
 
@@ -281,8 +329,7 @@ class Tester(object):
         with torch.no_grad():
             pre = self.crop_preprocessor()
             idx = window_index(0, n, n, self.num_phase).to(device=device, dtype=torch.int32)
-            diffs = self.phase_difference_extractor.phase_difference_indexed(pre.gray(frames), idx)
-            phase = [d.view(n, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+            streams = self._phase_streams(pre.gray(frames), idx)
             feats = self.resnet50_extractor.features_from_crops(frames, pre)
             ranges = snippet_ranges(n, self.length, self.stride)
             out = torch.zeros((n, len(self.label_name)), dtype=torch.float32, device=device)
@@ -290,9 +337,7 @@ class Tester(object):
                 batch = ranges[b0:b0 + self.batch_size]
                 rows = torch.cat([torch.arange(s, e, device=device) for s, e in batch])
                 L = batch[0][1] - batch[0][0]
-                p0 = phase[0].index_select(0, rows).view(len(batch), L, *phase[0].shape[1:])
-                p1 = phase[1].index_select(0, rows).view(len(batch), L, *phase[1].shape[1:])
-                pred = self.model([p0, p1], feats.index_select(0, rows).view(len(batch), L, -1))
+                pred = self._head(streams, rows, feats, len(batch), L)
                 for k, (s, e) in enumerate(batch):                        # in order: the tail snippet overwrites its overlap
                     out[s:e] = pred[k]
         return out
@@ -330,8 +375,7 @@ class Tester(object):
                                      for v, o in zip(group, offs)])
                     self._window_index[key] = idx.to(device=device, dtype=torch.int32)
                 idx = self._window_index[key]
-                diffs = self.phase_difference_extractor.phase_difference_indexed(pre.gray(frames), idx)
-                phase = [d.view(total, -1, d.shape[-2], d.shape[-1]) for d in diffs]
+                streams = self._phase_streams(pre.gray(frames), idx)
                 feats = self.resnet50_extractor.features_from_crops(frames, pre)
                 for v, o, k in zip(group, offs, range(i, j)):
                     n = v.shape[0]
@@ -342,13 +386,10 @@ class Tester(object):
                         L = batch[0][1] - batch[0][0]
                         whole = all(e - s == L and s == batch[0][0] + q * L for q, (s, e) in enumerate(batch))
                         if whole:                                             # consecutive snippets: plain views, no gather
-                            lo, hi = o + batch[0][0], o + batch[-1][1]
-                            p0, p1, ft = phase[0][lo:hi], phase[1][lo:hi], feats[lo:hi]
+                            rows = slice(o + batch[0][0], o + batch[-1][1])
                         else:
                             rows = torch.cat([torch.arange(o + s, o + e, device=device) for s, e in batch])
-                            p0, p1, ft = phase[0].index_select(0, rows), phase[1].index_select(0, rows), feats.index_select(0, rows)
-                        pred = self.model([p0.reshape(len(batch), L, *phase[0].shape[1:]),
-                                           p1.reshape(len(batch), L, *phase[1].shape[1:])], ft.reshape(len(batch), L, -1))
+                        pred = self._head(streams, rows, feats, len(batch), L)
                         for q, (s, e) in enumerate(batch):
                             pred_v[s:e] = pred[q]
                     out[k] = pred_v

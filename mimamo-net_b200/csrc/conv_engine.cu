@@ -1700,9 +1700,15 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
 }
 
 int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc, const void* residual,
-                 int ld_res, cudaStream_t stream) {
-  if (L.ksize == 1 && L.stride == 1 && L.pad == 0)
+                 int ld_res, cudaStream_t stream, int in_pitch, int in_channels) {
+  if (in_pitch == 0) in_pitch = L.Cin_p;
+  if (in_channels == 0) in_channels = L.Cin_p;
+  MM_REQUIRE(in_pitch % 8 == 0 && in_channels >= 1 && in_channels <= L.Cin_p && in_channels <= in_pitch, MIMAMO_E_VALUE,
+             "bad input pitch / channel count (%d / %d for %d padded channels)", in_pitch, in_channels, L.Cin_p);
+  if (L.ksize == 1 && L.stride == 1 && L.pad == 0) {
+    MM_REQUIRE(in_pitch == L.Cin_p && in_channels == L.Cin_p, MIMAMO_E_VALUE, "flat 1x1 layers need the dense Cin_p input layout");
     return gemm_forward(L, x, B * H * W, out, ldc, residual, ld_res, stream);
+  }
   MM_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ld_res % 8 == 0), MIMAMO_E_VALUE, "row pitches must be multiples of 8");
   if (B == 0) return MIMAMO_OK;
   const int Ho = out_size(H, L.ksize, L.stride, L.pad), Wo = out_size(W, L.ksize, L.stride, L.pad);
@@ -1715,8 +1721,8 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
     while ((bh + 2) * line > kHaloABytes / 128) --bh;
     if (bh >= 1) {
       CUtensorMap ma, mb;
-      const uint64_t dims[4] = {(uint64_t)L.Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-      const uint64_t strides[3] = {(uint64_t)L.Cin_p * 2, (uint64_t)W * L.Cin_p * 2, (uint64_t)H * W * L.Cin_p * 2};
+      const uint64_t dims[4] = {(uint64_t)in_channels, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)in_pitch * 2, (uint64_t)W * in_pitch * 2, (uint64_t)H * W * in_pitch * 2};
       const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)line, (uint32_t)(bh + 2), 1};
       const uint32_t es[4] = {1, 1, 1, 1};
       int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
@@ -1754,13 +1760,26 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
       return bf ? launch_halo_cfg<128, true>(ma, mb, mo, p, stream) : launch_halo_cfg<128, false>(ma, mb, mo, p, stream);
     }
   }
+  // Strided 1x1 layers (ResNet50's stride-2 `_reduce` / `_proj`): the layer only reads every stride-th pixel of every
+  // stride-th row, which is a DENSE box over a strided VIEW of the tensor (global strides multiplied by the stride) --
+  // TMA element strides (traversal strides) make the unit walk the skipped pixels as well (measured: those layers ran at
+  // 61 % of their floor).  MIMAMO_STRIDED_VIEW=0 restores the element-stride boxes (cross-check).
+  int vstride = L.stride;                       // stride still expressed through the box / element strides
+  int Wv = W, Hv = H;                           // extent of the tensor the map describes
+  uint64_t pix_pitch = (uint64_t)in_pitch;      // elements between horizontally adjacent pixels of that tensor
+  {
+    const char* e = getenv("MIMAMO_STRIDED_VIEW");
+    if (L.ksize == 1 && L.pad == 0 && L.stride > 1 && !(e && e[0] == '0')) {
+      vstride = 1; Wv = Wo; Hv = Ho; pix_pitch = (uint64_t)in_pitch * L.stride;
+    }
+  }
   // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows
   int best_bw = 1, best_bh = 1, best_bn = 1;
   long long best_tiles = -1;
   for (int bw = 1; bw <= Wo && bw <= 128; ++bw) {
-    if (bw * L.stride > 256) break;
+    if (bw * vstride > 256) break;
     for (int bh = 1; bh <= Ho && bw * bh <= 128; ++bh) {
-      if (bh * L.stride > 256) break;
+      if (bh * vstride > 256) break;
       int bn = 1;
       if (bw == Wo && bh == Ho) { bn = 128 / (bw * bh); if (bn > B) bn = B; if (bn < 1) bn = 1; }
       const long long tiles = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((B + bn - 1) / bn);
@@ -1770,10 +1789,10 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
     }
   }
   CUtensorMap ma, mb;
-  const uint64_t dims[4] = {(uint64_t)L.Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  const uint64_t strides[3] = {(uint64_t)L.Cin_p * 2, (uint64_t)W * L.Cin_p * 2, (uint64_t)H * W * L.Cin_p * 2};
-  const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(best_bw * L.stride), (uint32_t)(best_bh * L.stride), (uint32_t)best_bn};
-  const uint32_t es[4] = {1, (uint32_t)L.stride, (uint32_t)L.stride, 1};
+  const uint64_t dims[4] = {(uint64_t)in_channels, (uint64_t)Wv, (uint64_t)Hv, (uint64_t)B};
+  const uint64_t strides[3] = {pix_pitch * 2, (uint64_t)W * in_pitch * 2 * (uint64_t)(L.stride / vstride), (uint64_t)H * W * in_pitch * 2};
+  const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(best_bw * vstride), (uint32_t)(best_bh * vstride), (uint32_t)best_bn};
+  const uint32_t es[4] = {1, (uint32_t)vstride, (uint32_t)vstride, 1};
   int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
   if (rc) return rc;
   ConvParams p;
@@ -1786,6 +1805,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.tiles_h = (Ho + best_bh - 1) / best_bh;
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
+  p.stride = vstride;                           // the producer steps boxes in units of the tensor the map describes
   p.pair = pair_wanted(bn_eff, p.num_k_blocks, p.m_tiles, false);
   if (p.pair == 2) p.idesc = make_idesc2(bn_eff, L.elem);
   rc = weight_map(L, &mb, p.pair ? bn_eff / 2 : bn_eff);

@@ -45,8 +45,11 @@ int conv_layer_quantize(ConvLayer& L, int mode, const float* mu);
 // x: NHWC 16-bit [B][H][W][Cin_p] (row pitch == Cin_p).  out: NHWC 16-bit, row pitch `ldc` elements,
 // written at channel offset 0 of `out` (pass out + offset for concatenation).  residual: optional,
 // same geometry as out with pitch ld_res.  Returns MIMAMO_OK or an error code.
+// in_pitch / in_channels (3x3 and strided layers only): the input tensor holds `in_channels` <= Cin_p channels per pixel at a
+// row pitch of `in_pitch` elements (a multiple of 8); the TMA box still spans Cin_p channels and the missing ones are
+// zero-filled by the tensor map's out-of-bounds handling instead of being stored.  0 = the default dense Cin_p layout.
 int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc,
-                 const void* residual, int ld_res, cudaStream_t stream);
+                 const void* residual, int ld_res, cudaStream_t stream, int in_pitch = 0, int in_channels = 0);
 
 // Plain GEMM view of the same kernel: A [M][K_p] 16-bit row-major (K_p multiple of 64).
 int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, const void* residual,

@@ -169,9 +169,12 @@ PhaseNetLayout phasenet_layout(const PhaseNetPart& P, int M) {
 }
 }  // namespace
 
-// phase_0 f32[M,cin0,48,48], phase_1 f32[M,cin0,24,24] -> out[m][0..256) at pitch ldo (the `feature=True` output)
+// phase_0 f32[M,cin0,48,48], phase_1 f32[M,cin0,24,24] -> out[m][0..256) at pitch ldo (the `feature=True` output).
+// Alternatively (a0_nhwc != nullptr) the inputs arrive as the phase tail writes them for this net: a0_nhwc f16
+// [M][48][48][a0_pitch] holding the cin0 level-0 channels, cat_nhwc f16 [M][24][24][128] holding the level-1 channels at
+// [64, 64 + cin0) and zeros above (channels [0,64) are overwritten here by conv_net[0][3]).
 static int phasenet_run(const PhaseNetPart& P, const float* phase_0, const float* phase_1, int M, float* out, int ldo,
-                        char* ws, cudaStream_t s) {
+                        char* ws, cudaStream_t s, const uint16_t* a0_nhwc = nullptr, int a0_pitch = 0, uint16_t* cat_nhwc = nullptr) {
   const PhaseNetLayout L = phasenet_layout(P, M);
   float* pool = (float*)(ws + L.pool);
   float* fc = (float*)(ws + L.fc);
@@ -181,9 +184,14 @@ static int phasenet_run(const PhaseNetPart& P, const float* phase_0, const float
     const int Mc = M - m0 < P.chunk ? M - m0 : P.chunk;
     void* a0 = ws + L.a0; void* a1 = ws + L.a1; void* cat = ws + L.cat; void* a2 = ws + L.a2;
     void* a3 = ws + L.a3; void* a4 = ws + L.a4; void* a5 = ws + L.a5;
-    rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
-    if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
-    if (!rc) rc = conv_forward(P.conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
+    if (a0_nhwc) {
+      cat = cat_nhwc + (size_t)m0 * 24 * 24 * 128;
+      rc = conv_forward(P.conv[0], a0_nhwc + (size_t)m0 * 48 * 48 * a0_pitch, Mc, 48, 48, a1, 64, nullptr, 0, s, a0_pitch, c0);
+    } else {
+      rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
+      if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
+      if (!rc) rc = conv_forward(P.conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
+    }
     if (!rc) rc = conv_forward(P.conv[1], a1, Mc, 48, 48, cat, 128, nullptr, 0, s);      // -> cat[..., 0:64], 24x24
     if (!rc) rc = conv_forward(P.conv[2], cat, Mc, 24, 24, a2, 128, nullptr, 0, s);
     if (!rc) rc = conv_forward(P.conv[3], a2, Mc, 24, 24, a3, 128, nullptr, 0, s);       // 12x12
@@ -267,9 +275,9 @@ extern "C" int mimamo_head_workspace_bytes(const mimamo_head* head, int32_t bs, 
   return MIMAMO_OK;
 }
 
-extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, const float* phase_1, const float* rgb,
-                                   int32_t bs, int32_t nf, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
-  MM_REQUIRE(h && phase_0 && phase_1 && rgb && out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
+static int head_forward_impl(const mimamo_head* h, const float* phase_0, const float* phase_1, const uint16_t* a0_nhwc, int a0_pitch,
+                             uint16_t* cat_nhwc, const float* rgb, int32_t bs, int32_t nf, float* out, void* workspace,
+                             size_t workspace_bytes, void* stream_) {
   const int M = bs * nf;
   if (M == 0) return MIMAMO_OK;
   MM_CHECK_DEVICE(h->device);
@@ -282,7 +290,7 @@ extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, c
   // spatial stream: MLP over the ResNet50 features -> feat[:, 0:256]
   int rc = mlp_run(h->mlp, rgb, M, feat, 512, (float*)(ws + L.mlp_tmp), s);
   // temporal stream: PhaseNet -> feat[:, 256:512]
-  if (!rc) rc = phasenet_run(h->pn, phase_0, phase_1, M, feat + 256, 512, ws + L.pn, s);
+  if (!rc) rc = phasenet_run(h->pn, phase_0, phase_1, M, feat + 256, 512, ws + L.pn, s, a0_nhwc, a0_pitch, cat_nhwc);
   // fusion + recurrence over dim 0 (= bs; the nf frames are the GRU batch)
   if (!rc) rc = linear_forward(h->transform, feat, 512, M, f2, 256, s);
   if (!rc) rc = linear_forward(h->xproj[0], f2, 256, M, xp, 768, s);
@@ -291,6 +299,23 @@ extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, c
   if (!rc) rc = gru_layer(xp, h->whhT[1], h->bhh[1], bs, nf, 128, y1, s);
   if (!rc) rc = linear_forward(h->classifier, y1, 256, M, out, 2, s);
   return rc;
+}
+
+extern "C" int mimamo_head_forward(const mimamo_head* h, const float* phase_0, const float* phase_1, const float* rgb,
+                                   int32_t bs, int32_t nf, float* out, void* workspace, size_t workspace_bytes, void* stream_) {
+  MM_REQUIRE(h && phase_0 && phase_1 && rgb && out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
+  return head_forward_impl(h, phase_0, phase_1, nullptr, 0, nullptr, rgb, bs, nf, out, workspace, workspace_bytes, stream_);
+}
+
+// Same forward, fed by mimamo_pyr_phase_indexed_nhwc16: the phase differences arrive as the fp16 NHWC operands PhaseNet's
+// first convolution and its skip concatenation read (phase_tail.cu), so no fp32 NCHW phase tensor is written or transposed.
+extern "C" int mimamo_head_forward_nhwc16(const mimamo_head* h, const void* phase0_nhwc, int32_t phase0_pitch, void* cat_nhwc,
+                                          const float* rgb, int32_t bs, int32_t nf, float* out, void* workspace,
+                                          size_t workspace_bytes, void* stream_) {
+  MM_REQUIRE(h && phase0_nhwc && cat_nhwc && rgb && out && bs >= 0 && nf >= 0, MIMAMO_E_VALUE, "bad arguments");
+  MM_REQUIRE(phase0_pitch % 8 == 0 && phase0_pitch >= h->pn.cin0, MIMAMO_E_VALUE, "phase_0 pitch must be a multiple of 8 and hold %d channels", h->pn.cin0);
+  return head_forward_impl(h, nullptr, nullptr, reinterpret_cast<const uint16_t*>(phase0_nhwc), phase0_pitch,
+                           reinterpret_cast<uint16_t*>(cat_nhwc), rgb, bs, nf, out, workspace, workspace_bytes, stream_);
 }
 
 // ---- the two streams on their own: MLP.forward / PhaseNet.forward (api/mimamo_net.py:22-26,79-95) ----

@@ -271,7 +271,7 @@ __global__ void channel_mean_finish_kernel(const double* __restrict__ partial, i
 int channel_means(const void* x, long long M, int C, int ld, float* mean_dev, double* scratch, size_t scratch_doubles, ElemType elem, cudaStream_t s) {
   if (M == 0 || C == 0) return MIMAMO_OK;
   int blocks = (int)(scratch_doubles / (size_t)C);
-  if (blocks > 1024) blocks = 1024;
+  if (blocks > 128) blocks = 128;
   MM_REQUIRE(blocks >= 1, MIMAMO_E_VALUE, "channel_means: scratch too small");
   const int rows_per_block = (int)((M + blocks - 1) / blocks);
   blocks = (int)((M + rows_per_block - 1) / rows_per_block);

@@ -12,6 +12,7 @@
 // frame in shared memory.  The 11x11 kernel exp(-(x^2+y^2)/8) is separable, so the blur is an
 // 11-tap row pass followed by an 11-tap column pass over zero-padded tiles.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -265,6 +266,248 @@ phase_tail_kernel(const float* __restrict__ coeff, float* __restrict__ out, doub
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-map variant (maps up to 56x56: every Tester / PhaseNet configuration), software pipelined over the frames.
+//
+// The tiled kernel above runs A (phase / unwrap) -> B (row blur) -> C (column blur, ratio, difference) -> reduce -> W (write)
+// strictly in sequence: five block-wide barriers per frame with a handful of pixels per thread between them, so the
+// warps mostly wait (ncu on round 1: issue-bound at 69 % with 2 CTAs per SM).  Here a frame's stages are spread over
+// two phases that each mix independent work of neighbouring frames,
+//     phase 1:  C(t)  +  A(t+1)  +  W(t-1)        phase 2:  B(t+1)  +  mean of C(t)'s sums
+// i.e. two barriers per frame and three times the work between them.  The blurred phases live in a ring of three maps
+// (C(t) writes slot t%3 and reads (t-1)%3; W(t-1) reads (t-1)%3 and (t-2)%3), the unwrap state only covers pixels of the
+// map (the halo is F.conv2d's zero padding), and the row pass skips the all-zero halo rows.
+//
+// NHWC16 = true is the PhaseNet feed: instead of fp32 [map][T-1][rows][cols] the differences leave as fp16 channels
+// band*(T-1) + t of an NHWC tensor [window][rows][cols][pitch] (channel offset c_off), four channels (8 bytes) per store,
+// which is exactly the operand PhaseNet's first convolution / the skip concatenation reads (api/mimamo_net.py:79-86) --
+// the fp32 NCHW tensor and its transposition never exist on that path.
+// ---------------------------------------------------------------------------------------------------------------
+struct MapGeom {
+  int T, rows, cols;
+  int trp, tcp, rin, cin;
+};
+
+constexpr int kMapThreads = 320;      // upper bound of the whole-map kernel's block size (two CTAs per SM keep ~100 registers each)
+
+template <bool NHWC16>
+__global__ void __launch_bounds__(kMapThreads, 2)
+phase_tail_map_kernel(const float* __restrict__ coeff, void* __restrict__ out_, const MapGeom g, const int* __restrict__ root,
+                      int nb, int coeff_T, int polar, int mode, int pitch, int c_off) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp, rows = g.rows, cols = g.cols;
+  const int n_in = rin * cin, n_out = trp * tcp, n_map = rows * cols;
+  const int n_map_p = (n_map + 3) & ~3;                          // keeps every array below 16-byte aligned
+  double* cum = reinterpret_cast<double*>(raw);                  // [n_map] running unwrap correction
+  float* prev = reinterpret_cast<float*>(cum + n_map_p);         // [n_map] previous raw phase
+  float* mp = prev + n_map_p;                                    // [n_in] mag * unwrapped phase (zero padded region)
+  float* mg = mp + n_in;                                         // [n_in] mag
+  float* hmp = mg + n_in;                                        // [rin][tcp] row-blurred (halo rows stay zero)
+  float* hmg = hmp + rin * tcp;
+  float* blur = hmg + rin * tcp;                                 // [3][trp][tcp] ring of blurred phases
+  __shared__ double red[2][2][kMapThreads / 32];                 // [t & 1][difference / phase][warp]
+  __shared__ float mean_s[2][2];
+
+  const long long map = blockIdx.x;
+  const long long win = map / nb;
+  const int band = (int)(map - win * nb);
+  const int T = g.T;
+  const int n_slots = mode == 0 ? T - 1 : (mode == 1 ? T : 2 * (T - 1));
+  const int nthr = blockDim.x;
+  const int groups = tcp >> 2;
+
+  for (int i = threadIdx.x; i < n_map; i += nthr) { cum[i] = 0.0; prev[i] = 0.f; }
+  for (int i = threadIdx.x; i < 2 * n_in + 2 * rin * tcp; i += nthr) mp[i] = 0.f;      // mp, mg, hmp, hmg are contiguous
+  float gk[kTaps];
+#pragma unroll
+  for (int d = 0; d < kTaps; ++d) gk[d] = c_gauss[d];
+  const int a_sq = nthr / cols, a_sr = nthr % cols;
+  const int b_sq = nthr / groups, b_sr = nthr % groups;
+  const int c_sq = nthr / tcp, c_sr = nthr % tcp;
+  __syncthreads();
+
+  // (A) phase, magnitude, unwrap over time of frame t -> mp / mg
+  auto stage_a = [&](int t) {
+    long long slot = (long long)map * T + t;
+    if (root != nullptr) {
+      const int r = root[win * T + t];
+      slot = ((long long)(r / coeff_T) * nb + band) * coeff_T + (r % coeff_T);
+    }
+    const float2* src = reinterpret_cast<const float2*>(coeff) + (size_t)slot * n_map;
+    DivMod ia;
+    ia.init(threadIdx.x, cols);
+    for (int i0 = threadIdx.x; i0 < n_map; i0 += 4 * nthr) {
+      float2 v[4];
+      int cell[4], idx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        cell[u] = -1;
+        if (i < n_map) {
+          idx[u] = i;
+          cell[u] = (kHalo + ia.q) * cin + kHalo + ia.r;
+          v[u] = __ldg(src + i);
+        }
+        ia.step(a_sq, a_sr, cols);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (cell[u] < 0) continue;
+        const float ph = polar ? v[u].x : atan2f(v[u].y, v[u].x);
+        const float mag = polar ? v[u].y : __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v[u].y, v[u].y), __fmul_rn(v[u].x, v[u].x))), 1e-10f);
+        float up = ph;
+        if (t > 0) {
+          const double c = cum[idx[u]] + (double)unwrap_correction(__fsub_rn(ph, prev[idx[u]]));   // torch CPU cumsum: double acc
+          cum[idx[u]] = c;
+          up = __fadd_rn(ph, (float)c);
+        }
+        prev[idx[u]] = ph;
+        mp[cell[u]] = __fmul_rn(mag, up);
+        mg[cell[u]] = mag;
+      }
+    }
+  };
+  // (B) row pass over the map's own rows: 4 adjacent outputs per thread from 16 loaded inputs
+  auto stage_b = [&]() {
+    DivMod ib;
+    ib.init(threadIdx.x, groups);
+    for (int i = threadIdx.x; i < rows * groups; i += nthr, ib.step(b_sq, b_sr, groups)) {
+      const int ry = kHalo + ib.q, xg = ib.r << 2;
+      const float4* pa = reinterpret_cast<const float4*>(mp + ry * cin + xg);
+      const float4* pb = reinterpret_cast<const float4*>(mg + ry * cin + xg);
+      float a[16], b[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 va = pa[q], vb = pb[q];
+        a[4 * q] = va.x; a[4 * q + 1] = va.y; a[4 * q + 2] = va.z; a[4 * q + 3] = va.w;
+        b[4 * q] = vb.x; b[4 * q + 1] = vb.y; b[4 * q + 2] = vb.z; b[4 * q + 3] = vb.w;
+      }
+      float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int d = 0; d < kTaps; ++d)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { sa[o] = fmaf(gk[d], a[o + d], sa[o]); sb[o] = fmaf(gk[d], b[o + d], sb[o]); }
+      *reinterpret_cast<float4*>(hmp + ry * tcp + xg) = make_float4(sa[0], sa[1], sa[2], sa[3]);
+      *reinterpret_cast<float4*>(hmg + ry * tcp + xg) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+    }
+  };
+  // (C) column pass (4 vertically adjacent outputs per thread), ratio -> blur[t % 3]; sums of the difference and the phase
+  auto stage_c = [&](int t, double& part, double& part_ph) {
+    float* cur = blur + (t % 3) * n_out;
+    const float* old = blur + ((t + 2) % 3) * n_out;
+    const int ygroups = trp >> 2;
+    DivMod ic;
+    ic.init(threadIdx.x, tcp);
+    for (int i = threadIdx.x; i < ygroups * tcp; i += nthr, ic.step(c_sq, c_sr, tcp)) {
+      const int yg = ic.q << 2, x = ic.r;
+      float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 14; ++r) {
+        const float a = hmp[(yg + r) * tcp + x], b = hmg[(yg + r) * tcp + x];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int d = r - o;
+          if (d >= 0 && d < kTaps) { sa[o] = fmaf(gk[d], a, sa[o]); sb[o] = fmaf(gk[d], b, sb[o]); }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int y = yg + o;
+        if (y < rows && x < cols) {
+          const float val = __fdiv_rn(sa[o], sb[o]);
+          const int cell = y * tcp + x;
+          if (t > 0) part += (double)__fsub_rn(val, old[cell]);
+          cur[cell] = val;
+          part_ph += (double)val;
+        }
+      }
+    }
+  };
+  // output slots fed by frame t: the difference (t-1, t) and / or the denoised phase of frame t
+  auto slots_of = [&](int t, int& slot_d, int& slot_p) {
+    slot_d = -1; slot_p = -1;
+    if (mode == 0) { if (t > 0) slot_d = t - 1; }
+    else if (mode == 1) slot_p = t;
+    else if (t > 0) {
+      if (2 * (t - 1) < T - 1) slot_d = 2 * (t - 1);
+      if (2 * (t - 1) + 1 < T - 1) slot_p = 2 * (t - 1) + 1;
+    }
+  };
+  const float lim = 15.7079632679489656f;                          // 5*pi
+  constexpr int kMaxOwned = NHWC16 ? 12 : 1;                      // pixels per thread: 56 * 56 / 288 rounded up
+  uint32_t lo[kMaxOwned], hi[kMaxOwned];                          // NHWC16: four fp16 channels per owned pixel being collected
+  // (W) results of frame t: mean removal, clamp, store
+  auto stage_w = [&](int t) {
+    int slot_d, slot_p;
+    slots_of(t, slot_d, slot_p);
+    const float* cur = blur + (t % 3) * n_out;
+    const float* old = blur + ((t + 2) % 3) * n_out;
+    if (NHWC16) {
+      if (slot_d < 0) return;
+      const float mean = mean_s[t & 1][0];
+      const int sub = slot_d & 3;                                  // block-uniform
+      DivMod iw;
+      iw.init(threadIdx.x, cols);
+#pragma unroll
+      for (int k = 0; k < kMaxOwned; ++k, iw.step(a_sq, a_sr, cols)) {
+        const int i = threadIdx.x + k * nthr;
+        if (i < n_map) {
+          const int cell = iw.q * tcp + iw.r;
+          const float v = fminf(fmaxf(__fsub_rn(__fsub_rn(cur[cell], old[cell]), mean), -lim), lim);
+          const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(v));
+          if (sub == 0) { lo[k] = h; hi[k] = 0u; }
+          else if (sub == 1) lo[k] |= h << 16;
+          else if (sub == 2) hi[k] = h;
+          else {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(out_) + ((size_t)win * n_map + i) * pitch + c_off + band * (T - 1) + (slot_d - 3);
+            *reinterpret_cast<uint2*>(dst) = make_uint2(lo[k], hi[k] | (h << 16));
+          }
+        }
+      }
+      return;
+    }
+    float* out = reinterpret_cast<float*>(out_);
+    for (int which = 0; which < 2; ++which) {
+      const int slot = which == 0 ? slot_d : slot_p;
+      if (slot < 0) continue;
+      const float mean = mean_s[t & 1][which];
+      float* dst = out + ((size_t)map * n_slots + slot) * n_map;
+      DivMod iw;
+      iw.init(threadIdx.x, cols);
+      for (int i = threadIdx.x; i < n_map; i += nthr, iw.step(a_sq, a_sr, cols)) {
+        const int cell = iw.q * tcp + iw.r;
+        float v;
+        if (which == 0) v = fminf(fmaxf(__fsub_rn(__fsub_rn(cur[cell], old[cell]), mean), -lim), lim);
+        else v = __fsub_rn(cur[cell], mean);
+        dst[i] = v;
+      }
+    }
+  };
+
+  stage_a(0);
+  __syncthreads();
+  stage_b();
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    double part = 0.0, part_ph = 0.0;
+    stage_c(t, part, part_ph);
+    if (t + 1 < T) stage_a(t + 1);
+    if (t > 0) stage_w(t - 1);
+    part = warp_sum(part);
+    part_ph = warp_sum(part_ph);
+    if ((threadIdx.x & 31) == 0) { red[t & 1][0][threadIdx.x >> 5] = part; red[t & 1][1][threadIdx.x >> 5] = part_ph; }
+    __syncthreads();
+    if (t + 1 < T) stage_b();
+    if (threadIdx.x < 2) {
+      double tot = 0.0;
+      for (int i = 0; i < (nthr >> 5); ++i) tot += red[t & 1][threadIdx.x][i];
+      mean_s[t & 1][threadIdx.x] = (float)(tot / (double)n_map);
+    }
+    __syncthreads();
+  }
+  stage_w(T - 1);
+}
+
 // Tiled maps only: subtract the map mean (fixed-order sum of the tile partials) and clamp the differences.
 __global__ void phase_tail_finish_kernel(float* __restrict__ out, const double* __restrict__ partial,
                                          int ntiles, long long plane, int n_slots, int active_slots, int mode) {
@@ -304,6 +547,36 @@ static size_t tail_smem(const TailGeom& g) {
          2 * (size_t)g.trp * g.tcp * sizeof(float);
 }
 
+static MapGeom make_map_geom(int T, int rows, int cols) {
+  MapGeom g;
+  g.T = T; g.rows = rows; g.cols = cols;
+  g.trp = (rows + 3) / 4 * 4;
+  g.tcp = (cols + 3) / 4 * 4;
+  g.rin = g.trp + 2 * kHalo;
+  g.cin = g.tcp + 12;
+  return g;
+}
+
+static size_t map_smem(const MapGeom& g) {
+  const size_t n_map_p = ((size_t)g.rows * g.cols + 3) & ~(size_t)3;
+  return n_map_p * (sizeof(double) + sizeof(float)) +
+         sizeof(float) * (2 * (size_t)g.rin * g.cin + 2 * (size_t)g.rin * g.tcp + 3 * (size_t)g.trp * g.tcp);
+}
+
+static int tail_threads(int rows, int cols) {     // tiled kernel; small maps: fewer idle threads per barrier
+  return rows * cols >= 1600 ? kTailThreads : (rows * cols >= 400 ? 256 : 128);
+}
+
+// Whole-map kernel: the two blur passes each have (rows / 4) * cols work items (4 outputs each); pick the block size that
+// divides them evenly (48x48: 576 items -> 288 threads x 2; with 512 threads the second round ran 64 threads of 512).
+static int map_threads(const MapGeom& g) {
+  const int items = (g.trp >> 2) * g.tcp;
+  for (int k = 1;; ++k) {
+    const int t = ((items + k - 1) / k + 31) / 32 * 32;
+    if (t <= kMapThreads) return t < 64 ? 64 : t;
+  }
+}
+
 static DeviceOnce g_tail_ready;               // the __constant__ taps and the function attribute are per device
 static int tail_setup() {
   if (!g_tail_ready.need()) return MIMAMO_OK;
@@ -311,6 +584,8 @@ static int tail_setup() {
   for (int d = 0; d < kTaps; ++d) taps[d] = (float)exp(-(double)((d - kHalo) * (d - kHalo)) / 8.0);   // std = 2
   MM_CUDA(cudaMemcpyToSymbol(c_gauss, taps, sizeof(taps)));
   MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
   g_tail_ready.mark();
   return MIMAMO_OK;
 }
@@ -332,8 +607,16 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   MM_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
   MM_REQUIRE(n_maps < (1ll << 31) && ntiles < 65536, MIMAMO_E_VALUE, "batch too large for one launch");
   dim3 grid((unsigned)n_maps, (unsigned)ntiles);
-  const int threads = g.tile_r * g.tile_c >= 1600 ? kTailThreads : (g.tile_r * g.tile_c >= 400 ? 256 : 128);   // small maps: fewer idle threads per barrier
+  const int threads = tail_threads(g.tile_r, g.tile_c);
   if (mode == 2) MM_CUDA(cudaMemsetAsync(out, 0, (size_t)n_maps * n_slots * rows * cols * sizeof(float), stream));
+  const char* force = getenv("MIMAMO_TAIL");       // "tiled": run whole maps through the tiled kernel too (cross-check)
+  if (ntiles == 1 && !(force && force[0] == 't')) {
+    const MapGeom mgeo = make_map_geom(T, rows, cols);
+    phase_tail_map_kernel<false><<<(unsigned)n_maps, map_threads(mgeo), map_smem(mgeo), stream>>>(coeff, out, mgeo, root, nb, coeff_T > 0 ? coeff_T : T,
+                                                                                        polar, mode, 0, 0);
+    MM_LAUNCH_OK();
+    return MIMAMO_OK;
+  }
   phase_tail_kernel<<<grid, threads, tail_smem(g), stream>>>(coeff, out, (double*)workspace, g, root, nb, coeff_T > 0 ? coeff_T : T, polar, mode);
   MM_LAUNCH_OK();
   if (ntiles > 1) {
@@ -343,6 +626,27 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
     phase_tail_finish_kernel<<<fgrid, 256, 0, stream>>>(out, (const double*)workspace, ntiles, plane, n_slots, mode == 2 ? T - 1 : n_slots, mode);
     MM_LAUNCH_OK();
   }
+  return MIMAMO_OK;
+}
+
+// PhaseNet feed: the T-1 phase differences of every (window, band) map as fp16 channels band*(T-1) + t of the NHWC tensor
+// out16[window][rows][cols][pitch] at channel offset c_off.  Whole-map tiles and (T-1) % 4 == 0 only (callers fall back to
+// the fp32 output + transposition otherwise).
+bool phase_extract_nhwc16_supported(int T, int rows, int cols, int pitch, int c_off) {
+  return T >= 2 && (T - 1) % 4 == 0 && rows <= kWholeMapMax && cols <= kWholeMapMax && pitch % 4 == 0 && c_off % 4 == 0;
+}
+
+int phase_extract_nhwc16_launch(const float* coeff, int64_t n_maps, int T, int rows, int cols, void* out16, int pitch, int c_off,
+                                cudaStream_t stream, const int* root, int nb, int coeff_T, int polar) {
+  MM_REQUIRE(coeff && out16 && n_maps >= 0 && n_maps < (1ll << 31), MIMAMO_E_VALUE, "bad arguments");
+  MM_REQUIRE(phase_extract_nhwc16_supported(T, rows, cols, pitch, c_off), MIMAMO_E_RUNTIME, "fp16 NHWC phase output needs whole-map tiles and (T-1) %% 4 == 0");
+  if (n_maps == 0) return MIMAMO_OK;
+  int rc = tail_setup();
+  if (rc) return rc;
+  const MapGeom mgeo = make_map_geom(T, rows, cols);
+  phase_tail_map_kernel<true><<<(unsigned)n_maps, map_threads(mgeo), map_smem(mgeo), stream>>>(coeff, out16, mgeo, root, nb,
+                                                                                                 coeff_T > 0 ? coeff_T : T, polar, 0, pitch, c_off);
+  MM_LAUNCH_OK();
   return MIMAMO_OK;
 }
 
@@ -542,4 +846,34 @@ extern "C" int mimamo_pyr_phase_indexed(const mimamo_pyr_plan* plan, const float
     if (rc) return rc;
   }
   return MIMAMO_OK;
+}
+
+// Clip path feeding PhaseNet directly: as mimamo_pyr_phase_indexed, but the phase differences of level i leave as fp16
+// channels of the NHWC tensor out16[i] = [n_windows][c_i][c_i][pitch[i]] at channel offset c_off[i] (channel = band*(T-1) + t,
+// the order Tester.phase_diff_output's view produces, api/tester.py:131-138).  Same kernels and the same rounding as the
+// fp32 route followed by the head's own fp32 -> fp16 transposition, hence bit-identical network inputs.
+extern "C" int mimamo_pyr_phase_indexed_nhwc16(const mimamo_pyr_plan* plan, const float* frames, int64_t n_frames,
+                                               const int32_t* window_index, int64_t n_windows, int32_t T, void* const* out16,
+                                               const int32_t* pitch, const int32_t* c_off, void* workspace, size_t workspace_bytes,
+                                               void* stream) {
+  MM_REQUIRE(plan && out16 && pitch && c_off && n_frames >= 0 && n_windows >= 0 && T >= 2, MIMAMO_E_VALUE, "bad arguments");
+  if (n_windows == 0) return MIMAMO_OK;
+  MM_REQUIRE(frames && window_index && n_frames >= 1, MIMAMO_E_VALUE, "windows need at least one frame");
+  size_t coff[MIMAMO_MAX_LEVELS], toff, total;
+  int nl, nb, crops[MIMAMO_MAX_LEVELS];
+  indexed_layout(plan, n_frames, n_windows, T, coff, &toff, &total, &nl, &nb, crops);
+  MM_REQUIRE(workspace && workspace_bytes >= total, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", total);
+  MM_REQUIRE(n_frames < (1ll << 31) && n_windows * T < (1ll << 31), MIMAMO_E_VALUE, "too many frames for one call");
+  for (int i = 0; i < nl; ++i) {
+    MM_REQUIRE(out16[i], MIMAMO_E_VALUE, "null output for level %d", i);
+    MM_REQUIRE(phase_extract_nhwc16_supported(T, crops[i], crops[i], pitch[i], c_off[i]) && c_off[i] + nb * (T - 1) <= pitch[i],
+               MIMAMO_E_RUNTIME, "level %d (%dx%d maps, T = %d, pitch %d, offset %d) has no fp16 NHWC output path", i, crops[i], crops[i], T, pitch[i], c_off[i]);
+  }
+  float* cptr[MIMAMO_MAX_LEVELS];
+  for (int i = 0; i < nl; ++i) cptr[i] = reinterpret_cast<float*>((char*)workspace + coff[i]);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pyr_build_launch(plan, frames, n_frames, 1, cptr, nullptr, (char*)workspace + toff, total - toff, st, 1);
+  for (int i = 0; i < nl && !rc; ++i)
+    rc = phase_extract_nhwc16_launch(cptr[i], n_windows * nb, T, crops[i], crops[i], out16[i], pitch[i], c_off[i], st, window_index, nb, 1, 1);
+  return rc;
 }

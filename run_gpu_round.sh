@@ -25,7 +25,7 @@ print('$c: ms/step %.2f'%d['ms_per_step'], 'value %.0f %s'%(d['value'], d['unit'
 PY
 done
 if [ -n "$NCU_LIST" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c ${NCU_COUNT:-90} --csv --log-file gpurun_out/launches.csv python bench.py --quick --steps 1 --warmup 0 ${NCU_BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_LIST_SKIP:-0} -c ${NCU_COUNT:-90} --csv --log-file gpurun_out/launches.csv python bench.py --quick --steps 1 --warmup 0 ${NCU_BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"
 fi
 if [ -n "$NCU_FULL" ]; then
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$NCU_FULL" -s ${NCU_SKIP:-0} -c ${NCU_FULL_COUNT:-3} -o gpurun_out/prof_full -f python bench.py --quick --steps 1 --warmup 0 ${NCU_BENCH_ARGS:-} > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"

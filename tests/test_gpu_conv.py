@@ -18,8 +18,9 @@ CASES = [
     (2, 28, 28, 128, 128, 3, 1, 1, 1, False),
     (3, 14, 14, 256, 256, 3, 1, 1, 1, False),
     (5, 7, 7, 512, 512, 3, 1, 1, 1, False),      # two images per box
-    (2, 56, 56, 256, 128, 1, 2, 0, 1, False),    # strided 1x1 (TMA element strides)
+    (2, 56, 56, 256, 128, 1, 2, 0, 1, False),    # strided 1x1: dense boxes over a strided view of the tensor
     (2, 56, 56, 256, 512, 1, 2, 0, 0, False),
+    (3, 7, 9, 256, 512, 1, 2, 0, 0, False),      # odd extents: the view ends on the last sampled pixel
     (2, 48, 48, 64, 64, 3, 2, 1, 1, False),      # PhaseNet stride-2 3x3
     (3, 12, 12, 256, 256, 3, 2, 1, 1, False),
     (2, 14, 14, 256, 1024, 1, 1, 0, 1, True),    # residual add + ReLU epilogue

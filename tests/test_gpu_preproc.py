@@ -131,3 +131,25 @@ def test_video_path_matches_reference_semantics(cuda, n_frames, batch_size):
     assert len(both) == 2 and torch.equal(both[0].cpu(), got) and both[1].shape == (n2, 2)
     with pytest.raises(ValueError):
         t.predict_frames(torch.zeros(0, 112, 112, 3, dtype=torch.uint8, device=cuda))
+
+
+def test_fp16_operand_route_is_bit_identical(cuda, monkeypatch):
+    """Tester feeds PhaseNet the phase tail's fp16 NHWC output directly (mimamo_pyr_phase_indexed_nhwc16 ->
+    mimamo_head_forward_nhwc16); forcing the reference-shaped fp32 phase tensors (MIMAMO_PHASE_FP32=1: fp32 NCHW maps +
+    the head's own transposition) must give the same predictions bit for bit, on every entry point."""
+    from tester import Tester
+    B, Fr = 3, 20
+    crops = torch.from_numpy(_crops(B * Fr, 23).reshape(B, Fr, 112, 112, 3))
+    net = O.resnet_synthetic(1)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(), seed=1)
+    t = Tester(None, batch_size=2, resnet_model=net, head_state_dict=sd)
+    video = crops.reshape(B * Fr, 112, 112, 3)[:50]
+    monkeypatch.delenv("MIMAMO_PHASE_FP32", raising=False)
+    fast = (t.infer_crops(crops.to(cuda)), t.infer_crops_host(crops.pin_memory(), to_host=False), t.predict_frames(video.to(cuda)),
+            t.predict_videos([video.to(cuda), video[:30].to(cuda)])[1])
+    assert t._operand_buffers(B * Fr, cuda) is not None            # the operand route is the one that ran
+    monkeypatch.setenv("MIMAMO_PHASE_FP32", "1")
+    slow = (t.infer_crops(crops.to(cuda)), t.infer_crops_host(crops.pin_memory(), to_host=False), t.predict_frames(video.to(cuda)),
+            t.predict_videos([video.to(cuda), video[:30].to(cuda)])[1])
+    for a, b in zip(fast, slow):
+        assert a.shape == b.shape and torch.equal(a, b)
