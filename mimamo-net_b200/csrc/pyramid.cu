@@ -203,12 +203,134 @@ __device__ void band_outer(const LevelDev& L, const float* W, int band0, int n_b
   }
 }
 
+// ---- large frames (operands in the per-CTA global scratch): block products staged through shared memory ----
+// With the operands in global memory the register-tile loops above re-read every element of A and B from L1/L2 once per
+// 4x8 tile (28-56 times at 224x224): the 224x224 configuration ran on the L2 -> SM path (16 TFLOP/s).  Here the CTA
+// computes one (16*TM) x (16*TN) block at a time, K in chunks of 16 staged through shared memory (register prefetch of the
+// next chunk), so each operand element crosses L2 -> SM once per block.  A thread's TN = 8 columns are two groups of four
+// (j and j + 64), which keeps every float4 shared-memory read a contiguous 16-byte-per-lane wavefront.
+constexpr int kBK = 16;
+struct BlockSmem {
+  float a[kBK][128];
+  float b0[kBK][128];
+  float b1[kBK][128];
+};
+
+// acc0[r][c] (+acc1) += sum_k A[k*lda + i(r)] * mask * B0[k*ldb + j(c)],   i(r) = i0 + lane_i(r), j(c) = j0 + lane_j(c)
+// rows / columns beyond M / N read as zero.  BI = 16*TM, BJ = 16*TN; tiles of 8 are split as {4t..4t+3} u {64+4t..}.
+template <int TM, int TN, bool MASKED, bool DUAL>
+__device__ __forceinline__ void block_gemm(const float* __restrict__ A, int lda, const float* __restrict__ Mk, int ldm, int M,
+                                           const float* __restrict__ B0, const float* __restrict__ B1, int ldb, int N, int K,
+                                           int i0, int j0, BlockSmem& sm, float (&acc0)[TM][TN], float (&acc1)[TM][TN]) {
+  constexpr int BI = 16 * TM, BJ = 16 * TN;
+  constexpr int A4 = kBK * BI / 4 / kPyrThreads, B4 = kBK * BJ / 4 / kPyrThreads;      // float4 loads per thread per chunk
+  static_assert(A4 >= 1 && B4 >= 1, "block too small for 256 threads");
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  float4 ra[A4], rb0[B4], rb1[DUAL ? B4 : 1];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < A4; ++q) {
+      const int e = threadIdx.x + q * kPyrThreads, kk = e / (BI / 4), i = i0 + (e % (BI / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + kk < K && i < M) {
+        v = __ldg(reinterpret_cast<const float4*>(A + (size_t)(k0 + kk) * lda + i));
+        if (MASKED) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(Mk + (size_t)(k0 + kk) * ldm + i));
+          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        }
+      }
+      ra[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < B4; ++q) {
+      const int e = threadIdx.x + q * kPyrThreads, kk = e / (BJ / 4), j = j0 + (e % (BJ / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v;
+      if (k0 + kk < K && j < N) {
+        v = __ldg(reinterpret_cast<const float4*>(B0 + (size_t)(k0 + kk) * ldb + j));
+        if (DUAL) w = __ldg(reinterpret_cast<const float4*>(B1 + (size_t)(k0 + kk) * ldb + j));
+      }
+      rb0[q] = v;
+      if (DUAL) rb1[q] = w;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += kBK) {
+#pragma unroll
+    for (int q = 0; q < A4; ++q) {
+      const int e = threadIdx.x + q * kPyrThreads;
+      *reinterpret_cast<float4*>(&sm.a[e / (BI / 4)][(e % (BI / 4)) * 4]) = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < B4; ++q) {
+      const int e = threadIdx.x + q * kPyrThreads;
+      *reinterpret_cast<float4*>(&sm.b0[e / (BJ / 4)][(e % (BJ / 4)) * 4]) = rb0[q];
+      if (DUAL) *reinterpret_cast<float4*>(&sm.b1[e / (BJ / 4)][(e % (BJ / 4)) * 4]) = rb1[q];
+    }
+    __syncthreads();
+    if (k0 + kBK < K) fetch(k0 + kBK);                         // global loads of the next chunk fly during the FMAs
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      float av[TM], bv[TN], cv[DUAL ? TN : 1];
+#pragma unroll
+      for (int q = 0; q < TM / 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(&sm.a[kk][q * 64 + ti * 4]);
+        av[4 * q] = a.x; av[4 * q + 1] = a.y; av[4 * q + 2] = a.z; av[4 * q + 3] = a.w;
+      }
+#pragma unroll
+      for (int q = 0; q < TN / 4; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(&sm.b0[kk][q * 64 + tj * 4]);
+        bv[4 * q] = b.x; bv[4 * q + 1] = b.y; bv[4 * q + 2] = b.z; bv[4 * q + 3] = b.w;
+        if (DUAL) {
+          const float4 c = *reinterpret_cast<const float4*>(&sm.b1[kk][q * 64 + tj * 4]);
+          cv[4 * q] = c.x; cv[4 * q + 1] = c.y; cv[4 * q + 2] = c.z; cv[4 * q + 3] = c.w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) {
+          acc0[r][c] = fmaf(av[r], bv[c], acc0[r][c]);
+          if (DUAL) acc1[r][c] = fmaf(av[r], cv[c], acc1[r][c]);
+        }
+    }
+    __syncthreads();
+  }
+}
+
+// row / column of element (r, c) of a thread's tile inside its block (tiles of 8 are split in two groups of four)
+__device__ __forceinline__ int tile_off(int t, int r) { return (r >> 2) * 64 + t * 4 + (r & 3); }
+
+// C[i][j] = sum_k A[k][i] (* mask) B[k][j] for all i < M, j < N, written to C (leading dimension ldc); 64 x 128 blocks
+template <bool MASKED>
+__device__ void large_product(const float* A, int lda, const float* Mk, int ldm, int M, const float* B, int ldb, int N, int K,
+                              float* C, int ldc, BlockSmem& sm) {
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  for (int i0 = 0; i0 < M; i0 += 64)
+    for (int j0 = 0; j0 < N; j0 += 128) {
+      float acc[4][8], unused[4][8];
+      zero(acc);
+      block_gemm<4, 8, MASKED, false>(A, lda, Mk, ldm, M, B, nullptr, ldb, N, K, i0, j0, sm, acc, unused);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ti * 4 + r;
+        if (i >= M) continue;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int j = j0 + q * 64 + tj * 4;
+          if (j < N) *reinterpret_cast<float4*>(C + (size_t)i * ldc + j) = make_float4(acc[r][4 * q], acc[r][4 * q + 1], acc[r][4 * q + 2], acc[r][4 * q + 3]);
+        }
+      }
+    }
+}
+
 template <bool LARGE>
-__global__ void __launch_bounds__(kPyrThreads)
+__global__ void __launch_bounds__(kPyrThreads, 2)
 pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T,
                  const __grid_constant__ OutPtrs outs, const int* __restrict__ root, float* scratch, long long n_frames, int polar) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[32];
+  __shared__ __align__(16) BlockSmem bsm_storage[LARGE ? 1 : 0 + !LARGE];     // only the large-frame path uses it
+  BlockSmem& bsm = bsm_storage[0];
   // Small frames: one CTA per frame, everything in shared memory.  Large frames (H > ~128, e.g. the
   // 224x224 configuration): a persistent grid walks the frames and keeps the same buffers in a
   // private slice of a caller-provided global scratch (L2-resident), same code otherwise.
@@ -218,6 +340,76 @@ pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ fr
     if (root != nullptr && root[n] != (int)n) continue;    // duplicate of an earlier frame: its root's coefficients are reused
     const long long w = n / T;
     const int t = (int)(n - w * T);
+    auto emit = [&](float2* out, int b, int c, int y, int x, float re, float im) {
+      if (y >= c || x >= c) return;
+      float2 v = make_float2(re, im);
+      if (polar) {
+        // (phase, magnitude) exactly as the phase tail computes them from (re, im): the fused paths store the polar form
+        // once per distinct frame so that the 13 windows sharing it do not repeat the atan2 / sqrt
+        const float ph = atan2f(v.y, v.x);
+        const float mg = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+        v = make_float2(ph, mg);
+      }
+      out[((((size_t)w * P.nb + b) * T + t) * c + y) * (size_t)c + x] = v;
+    };
+    if (LARGE) {
+      // frame -> Xs (mean removed) in the scratch, then the same four products as block GEMMs
+      const int H = P.H, Hp = P.Hp, Kp = P.Kp;
+      float* Xs = W;
+      float* R1 = W + (size_t)Hp * Hp;
+      const float* frame = frames + (size_t)n * H * H;
+      float part = 0.f;
+      for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+        const int m = i / Hp, nn = i - m * Hp;
+        float v = 0.f;
+        if (m < H && nn < H) v = __ldg(frame + (size_t)m * H + nn);
+        Xs[i] = v;
+        part += v;
+      }
+      const float mean = block_sum(part, red) / (float)(H * H);
+      for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+        const int m = i / Hp, nn = i - m * Hp;
+        if (m < H && nn < H) Xs[i] -= mean;
+      }
+      __syncthreads();
+      large_product<false>(Xs, Hp, nullptr, 0, Hp, P.dct_t, Kp, Kp, Hp, R1, Kp, bsm);          // R1[n][k] = sum_m X[m][n] dct[m][k]
+      __syncthreads();
+      large_product<false>(P.dct_t, Kp, nullptr, 0, Kp, R1, Kp, Kp, Hp, Ct, Kp, bsm);          // Ct[l][k] = sum_n dct[n][l] R1[n][k]
+      __syncthreads();
+      for (int li = 0; li < P.n_levels; ++li) {
+        const LevelDev& L = P.lv[li];
+        float2* out = reinterpret_cast<float2*>(outs.p[li]);
+        const int c = L.c, hp = L.hp, cp = L.cp;
+        for (int band0 = 0; band0 < P.nb; band0 += L.units_per_chunk) {
+          const int n_bands = min(L.units_per_chunk, P.nb - band0);
+          for (int job = 0; job < n_bands * 4; ++job) {          // U[(band, ch)][half*hp + k][x]
+            const int u = job >> 1, half = job & 1, unit = band0 * 2 + u, b = unit >> 1, ch = unit & 1;
+            const float* mask = L.masks + ((size_t)((b * 2 + ch) * 2 + half) * hp) * hp;
+            const float* tab = L.trig + (size_t)L.inner_sel[ch][half] * hp * cp;
+            large_product<true>(Ct, Kp, mask, hp, hp, tab, cp, cp, hp, W + ((size_t)u * 2 * hp + half * hp) * cp, cp, bsm);
+          }
+          __syncthreads();
+          const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+          for (int u = 0; u < n_bands; ++u) {
+            const float* Bre = W + (size_t)(2 * u) * 2 * hp * cp;
+            const float* Bim = Bre + (size_t)2 * hp * cp;
+            for (int i0 = 0; i0 < cp; i0 += 128)
+              for (int j0 = 0; j0 < cp; j0 += 64) {
+                float re[8][4], im[8][4];
+                zero(re);
+                zero(im);
+                block_gemm<8, 4, false, true>(L.trig, cp, nullptr, 0, cp, Bre, Bim, cp, cp, 2 * hp, i0, j0, bsm, re, im);
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) emit(out, band0 + u, c, i0 + tile_off(ti, r), j0 + tj * 4 + q, re[r][q], im[r][q]);
+              }
+          }
+          __syncthreads();
+        }
+      }
+      continue;
+    }
     frame_spectrum(P, frames + (size_t)n * P.H * P.H, Ct, W, red);
     for (int li = 0; li < P.n_levels; ++li) {
       const LevelDev& L = P.lv[li];
@@ -228,26 +420,10 @@ pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ fr
         band_inner(P, L, Ct, W, band0, n_bands);
         __syncthreads();
         band_outer(L, W, band0, n_bands, [&](int b, int y0, int x0, const float (&re)[8][4], const float (&im)[8][4]) {
-          float2* base = out + ((((size_t)w * P.nb + b) * T + t) * c) * (size_t)c;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int y = y0 + r;
-            if (y >= c) continue;
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int x = x0 + q;
-              if (x >= c) continue;
-              float2 v = make_float2(re[r][q], im[r][q]);
-              if (polar) {
-                // (phase, magnitude) exactly as the phase tail computes them from (re, im): the fused paths store the
-                // polar form once per distinct frame so that the 13 windows sharing it do not repeat the atan2 / sqrt
-                const float ph = atan2f(v.y, v.x);
-                const float mg = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
-                v = make_float2(ph, mg);
-              }
-              base[(size_t)y * c + x] = v;
-            }
-          }
+            for (int q = 0; q < 4; ++q) emit(out, b, c, y0 + r, x0 + q, re[r][q], im[r][q]);
         });
         __syncthreads();
       }

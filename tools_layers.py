@@ -19,9 +19,11 @@ for path in sys.argv[1:]:
     lines = [l for l in open(path) if l.strip() and l.strip()[0].isdigit()]
     vals = [float(x) for x in lines[-1].split()]
     n = len(names)
-    chunk = [sum(vals[c * n + i] for c in range(4)) / 4 for i in range(n)]
+    passes = max(1, (len(vals) - 12) // n)                       # ResNet passes per step (2048 / images per pass)
+    B = 2048 // passes
+    chunk = [sum(vals[c * n + i] for c in range(passes)) / passes * (512.0 / B) for i in range(n)]      # per 512 images
     print("== %s: %d launches; ResNet chunk of %d images: %.0f us measured, %.0f us floor (sum of per-layer max(tensor, HBM))" % (path, len(vals), B, sum(chunk), sum(floors)))
     for nm, v, f in zip(names, chunk, floors):
         print("  %-12s %7.1f us  floor %6.1f  (%.0f%%)" % (nm, v, f, 100 * f / v))
-    rest = vals[4 * n:]
+    rest = vals[passes * n:]
     print("  head convs:", " ".join("%.0f" % v for v in rest))
