@@ -236,6 +236,11 @@ class Ctx(object):
         import torch.distributed as dist
         self.dist = dist
         self.args = args
+        # stdout carries exactly ONE JSON line: anything the libraries print on fd 1 meanwhile (NCCL's version banner, ...)
+        # is sent to stderr, and the line itself is written to the saved descriptor by finish()
+        sys.stdout.flush()
+        self._stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,7 +307,8 @@ class Ctx(object):
             if self.sampler.is_alive():
                 self.sampler.join(timeout=2)
             line["clocks"] = self.sampler.summary()
-            print(json.dumps(line))
+            sys.stdout.flush()
+            os.write(self._stdout_fd, (json.dumps(line) + "\n").encode())
         if self.world > 1:
             self.dist.destroy_process_group()
 

@@ -119,9 +119,18 @@ class Tester(object):
         video_name = os.path.basename(input_video).split('.')[0]
         opface_output_dir = os.path.join(os.path.dirname(input_video), video_name + "_opface")
         self.video_processor.process(input_video, opface_output_dir)
+        return self.test_aligned(opface_output_dir, video_name, os.path.join(os.path.dirname(input_video), video_name + "_pool5"), fast)
+
+    def test_aligned(self, opface_output_dir, video_name, feature_dir=None, fast=True):
+        """`test` from the OpenFace output directory on (reference :60-74): <dir>/<video>_aligned/frame_det_00_%06d.bmp ->
+        {video: DataFrame}.  fast=True decodes the crops once and runs everything on the device; fast=False is the
+        reference's file route (features to <feature_dir>/%05d.npy, PIL samplers, DataLoader).  Both give the same
+        numbers: the device transforms are bit-exact with PIL and every kernel is independent of the batch composition."""
+        from sampler.snippet_sampler import Snippet_Sampler
         if fast:
             return self.test_frames(load_aligned_crops(opface_output_dir, video_name), video_name)
-        feature_dir = os.path.join(os.path.dirname(input_video), video_name + "_pool5")
+        if feature_dir is None:
+            feature_dir = os.path.join(os.path.dirname(os.path.abspath(opface_output_dir)), video_name + "_pool5")
         self.resnet50_extractor.run(opface_output_dir, feature_dir, video_name=video_name)
         dataset = Snippet_Sampler(video_name, opface_output_dir, feature_dir, annot_dir=None,
                                   label_name='valence_arousal', test_mode=True, num_phase=self.num_phase,

@@ -117,6 +117,33 @@ __global__ void spec_scatter_kernel(const float2* __restrict__ B, int S, const i
   }
 }
 
+// Image means: the DC coefficient of an image with values in [0,1] is ~S^2/2 while every other coefficient is ~S/3, so
+// summing the raw image in fp32 spends the mantissa on the mean (the low residual, which carries it times (S/s)^2, came
+// out 5x less accurate than the reference's FFT).  The forward DFT therefore runs on x - mean and DC is restored exactly.
+__global__ void image_mean_kernel(const float* __restrict__ x, long long plane, float* __restrict__ centred, float* __restrict__ mean) {
+  __shared__ double red[32];
+  const float* p = x + (size_t)blockIdx.x * plane;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < plane; i += blockDim.x) acc += (double)__ldg(p + i);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    red[0] = tot / (double)plane;
+  }
+  __syncthreads();
+  const float m = (float)red[0];
+  if (threadIdx.x == 0) mean[blockIdx.x] = m;
+  float* q = centred + (size_t)blockIdx.x * plane;
+  for (long long i = threadIdx.x; i < plane; i += blockDim.x) q[i] = __ldg(p + i) - m;
+}
+__global__ void restore_dc_kernel(float2* __restrict__ F, long long plane, const float* __restrict__ mean, long long N) {
+  const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (n < N) F[(size_t)n * plane].x += mean[n] * (float)plane;
+}
+
 struct ScfUnit {
   int s, planes, is_real, twist_build, twist_recon;
   int* src;             // [s]
@@ -197,7 +224,7 @@ static size_t scf_plane_floats(const mimamo_scf_plan* plan, int64_t N) {
 
 extern "C" int mimamo_scf_workspace_bytes(const mimamo_scf_plan* plan, int64_t N, size_t* bytes_out) {
   MM_REQUIRE(plan && bytes_out && N >= 0, MIMAMO_E_VALUE, "bad arguments");
-  *bytes_out = 3 * align_up(scf_plane_floats(plan, N) * sizeof(float), 256) + 256;
+  *bytes_out = 3 * align_up(scf_plane_floats(plan, N) * sizeof(float), 256) + align_up((size_t)(N > 0 ? N : 1) * sizeof(float), 256) + 256;
   return MIMAMO_OK;
 }
 
@@ -233,8 +260,15 @@ extern "C" int mimamo_scf_build(const mimamo_scf_plan* plan, const float* images
   float* T2 = reinterpret_cast<float*>(base + 2 * plane);
   const int S = plan->S;
   // forward 2-D DFT of every image (torch.rfft(onesided=False), SCFpyr_PyTorch.py:110), natural frequency order
-  int rc = dft_pass<true, false>(images, T1, N, S, S, -1.f, 1.f, plan->tw_S, st);
+  float* means = reinterpret_cast<float*>(base + 3 * plane);
+  image_mean_kernel<<<(unsigned)N, 256, 0, st>>>(images, (long long)S * S, T2, means);
+  MM_LAUNCH_OK();
+  int rc = dft_pass<true, false>(T2, T1, N, S, S, -1.f, 1.f, plan->tw_S, st);
   if (!rc) rc = dft_pass<false, false>(T1, F, N, S, S, -1.f, 1.f, plan->tw_S, st);
+  if (!rc) {
+    restore_dc_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<float2*>(F), (long long)S * S, means, N);
+    MM_LAUNCH_OK();
+  }
   for (size_t i = 0; i < plan->units.size() && !rc; ++i) {
     const ScfUnit& u = plan->units[i];
     MM_REQUIRE(unit_out[i], MIMAMO_E_VALUE, "null output for pyramid unit %zu", i);

@@ -153,3 +153,29 @@ def test_fp16_operand_route_is_bit_identical(cuda, monkeypatch):
             t.predict_videos([video.to(cuda), video[:30].to(cuda)])[1])
     for a, b in zip(fast, slow):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_fast_and_file_routes_agree(cuda, tmp_path):
+    """Tester.test_aligned on a synthetic OpenFace output directory: fast=True (crops decoded once, every transform on the
+    device) against fast=False, the reference's file route (Resnet50_Extractor.run -> %05d.npy -> Snippet_Sampler with
+    PIL -> DataLoader -> test_on_dataloader, api/tester.py:60-74).  Same numbers bit for bit, and the file route leaves the
+    reference's feature cache behind."""
+    from PIL import Image
+    from tester import Tester
+    n = 70                                                    # one full snippet + the overlapping tail snippet
+    frames = _crops(n, 31)
+    aligned = tmp_path / "clip_opface" / "clip_aligned"
+    aligned.mkdir(parents=True)
+    for i in range(n):
+        Image.fromarray(frames[i]).save(str(aligned / ("frame_det_00_%06d.bmp" % (i + 1))))
+    net = O.resnet_synthetic(1)
+    sd = O.synthetic_state_dict(O.head_state_dict_spec(), seed=1)
+    t = Tester(None, batch_size=4, resnet_model=net, head_state_dict=sd)
+    fast = t.test_aligned(str(tmp_path / "clip_opface"), "clip", fast=True)
+    feature_dir = tmp_path / "clip_pool5"
+    slow = t.test_aligned(str(tmp_path / "clip_opface"), "clip", str(feature_dir), fast=False)
+    assert list(fast) == list(slow) == ["clip"]
+    a, b = fast["clip"].to_numpy(), slow["clip"].to_numpy()
+    assert a.shape == b.shape == (n, 2) and list(slow["clip"].columns) == ["valence", "arousal"]
+    assert np.array_equal(a, b)
+    assert len(list(feature_dir.glob("*.npy"))) == n and np.load(str(feature_dir / "00001.npy")).shape == (2048,)
