@@ -243,8 +243,9 @@ int  mimamo_head_forward_nhwc16(const mimamo_head* head, const void* phase0_nhwc
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* The two streams of the head on their own: MLP.forward (api/mimamo_net.py:22-26; keys `mlp.{1,2,5,6,...}`, any depth,
- * last width 256) and PhaseNet.forward for 48x48 inputs (:79-95; keys `conv_net.*`, `fc.*`, `classifier.*`).
- * x f32[rows, in_features] -> out f32[rows,256];  phase_0 f32[rows,C,48,48], phase_1 f32[rows,C,24,24] ->
+ * last width 256) and PhaseNet.forward (:27-95; keys `conv_net.*`, `fc.*`, `classifier.*`; input_size S = 48 with three
+ * conv blocks, 96 or 112 with four).
+ * x f32[rows, in_features] -> out f32[rows,256];  phase_0 f32[rows,C,S,S], phase_1 f32[rows,C,S/2,S/2] ->
  * out f32[rows,256] (feature != 0) or f32[rows,1] (feature == 0: + classifier Linear(256,1) + BatchNorm1d(1)). */
 typedef struct mimamo_mlp mimamo_mlp;
 int  mimamo_mlp_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, mimamo_mlp** mlp_out);
@@ -254,8 +255,8 @@ int  mimamo_mlp_workspace_bytes(const mimamo_mlp* mlp, int32_t rows, size_t* byt
 int  mimamo_mlp_forward(const mimamo_mlp* mlp, const float* x, int32_t rows, float* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 typedef struct mimamo_phasenet mimamo_phasenet;
-int  mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_channels,
-                            mimamo_phasenet** net_out);
+int  mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t input_size,
+                            int32_t num_channels, mimamo_phasenet** net_out);
 void mimamo_phasenet_destroy(mimamo_phasenet* net);
 int  mimamo_phasenet_workspace_bytes(const mimamo_phasenet* net, int32_t rows, size_t* bytes_out);
 int  mimamo_phasenet_forward(const mimamo_phasenet* net, const float* phase_0, const float* phase_1, int32_t rows,

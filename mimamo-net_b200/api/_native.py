@@ -96,7 +96,8 @@ _SIGNATURES = {
     "mimamo_mlp_in_features": (ctypes.c_int, [vp]),
     "mimamo_mlp_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_mlp_forward": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),
-    "mimamo_phasenet_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp)]),
+    "mimamo_phasenet_create": (ctypes.c_int, [ctypes.POINTER(TensorDesc), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.POINTER(vp)]),
     "mimamo_phasenet_destroy": (None, [vp]),
     "mimamo_phasenet_workspace_bytes": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t)]),
     "mimamo_phasenet_forward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, ctypes.c_size_t, vp]),

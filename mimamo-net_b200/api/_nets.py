@@ -168,19 +168,20 @@ class NativePhaseNet(_Handle):
     """PhaseNet.forward on its own (mimamo_phasenet_*): keys `conv_net.*`, `fc.*`, `classifier.*`."""
     _destroy = 'mimamo_phasenet_destroy'
 
-    def __init__(self, state_dict, num_channels):
+    def __init__(self, state_dict, num_channels, input_size=48):
         super().__init__()
         _native.require_cuda('PhaseNet')
         table, n, keep = _tensor_table(state_dict)
-        _native.check(_native.lib().mimamo_phasenet_create(table, n, num_channels, ctypes.byref(self.handle)))
+        _native.check(_native.lib().mimamo_phasenet_create(table, n, input_size, num_channels, ctypes.byref(self.handle)))
         self.channels = num_channels
+        self.size = input_size
 
     def forward(self, level0, level1, feature):
         rows = level0.shape[0]
         for t in (level0, level1):
             assert t.is_cuda and t.dtype == torch.float32, 'PhaseNet inputs must be float32 CUDA tensors'
-        assert tuple(level0.shape) == (rows, self.channels, 48, 48) and tuple(level1.shape) == (rows, self.channels, 24, 24), \
-            'unexpected PhaseNet input shapes'
+        assert tuple(level0.shape) == (rows, self.channels, self.size, self.size) and \
+            tuple(level1.shape) == (rows, self.channels, self.size // 2, self.size // 2), 'unexpected PhaseNet input shapes'
         level0, level1 = level0.contiguous(), level1.contiguous()
         out = torch.empty((rows, 256 if feature else 1), dtype=torch.float32, device=level0.device)
         lib = _native.lib()

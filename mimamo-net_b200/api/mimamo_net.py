@@ -47,17 +47,17 @@ class PhaseNet(nn.Module):
         super(PhaseNet, self).__init__()
         if input_size not in [48, 96, 112]:
             raise ValueError("Incorrect input size")
-        if input_size != 48:
-            raise NotImplementedError('only the 48x48 PhaseNet used by Two_Stream_RNN has CUDA kernels '
-                                      '(the 96 / 112 variants of api/mimamo_net.py:31-38 are built by no reference caller)')
         if list(hidden_units) != [256, 256, 1]:
             raise NotImplementedError('the CUDA PhaseNet is built for hidden_units=[256, 256, 1]')
         self.num_channels = num_channels
-        widths = [64, 128, 256]
-        ins = [num_channels, num_channels + 64, 128]
+        self.input_size = input_size
+        n_blocks = 3 if input_size == 48 else 4                    # reference :33-40
+        widths = [64 << b for b in range(n_blocks)]
+        ins = [num_channels, num_channels + 64] + widths[1:-1]
         self.conv_net = nn.ModuleList([self._block(i, o) for i, o in zip(ins, widths)])
         self.dropout = nn.Dropout2d(p=0.2)
-        self.avgpool = nn.AvgPool2d(kernel_size=[6, 6])
+        last_conv_width = 6 if input_size in (48, 96) else 7
+        self.avgpool = nn.AvgPool2d(kernel_size=[last_conv_width, last_conv_width])
         fc, prev = [], widths[-1]
         for h in hidden_units[:-1]:                                   # keys 0,2 / 4,6
             fc += [nn.Linear(prev, h), nn.ReLU(inplace=True), nn.BatchNorm1d(h), nn.Dropout(dropout)]
@@ -77,12 +77,12 @@ class PhaseNet(nn.Module):
         return super(PhaseNet, self).load_state_dict(*args, **kwargs)
 
     def forward(self, data_level0, data_level1):
-        """(bs, frames, C, 48, 48), (bs, frames, C, 24, 24) -> (bs*frames, 256) when `feature` else (bs*frames, 1), eval
+        """(bs, frames, C, S, S), (bs, frames, C, S/2, S/2) -> (bs*frames, 256) when `feature` else (bs*frames, 1), eval
         mode (reference :79-95), via mimamo_phasenet_forward."""
         if self.training:
             raise RuntimeError('PhaseNet (B200) is inference only: call .eval() first')
         if getattr(self, '_native', None) is None:
-            self._native = _nets.NativePhaseNet(self.state_dict(), self.num_channels)
+            self._native = _nets.NativePhaseNet(self.state_dict(), self.num_channels, self.input_size)
         bs, num_frames, num_channel, W0, H0 = data_level0.size()
         bs, num_frames, num_channel, W1, H1 = data_level1.size()
         with torch.no_grad():

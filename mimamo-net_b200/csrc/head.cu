@@ -21,10 +21,13 @@ struct MlpPart {
   std::vector<LinearLayer> layers;
   int in_f = 0, max_f = 0;
 };
-// PhaseNet for 48x48 inputs (api/mimamo_net.py:27-95)
+// PhaseNet (api/mimamo_net.py:27-95): input size 48 -> three conv blocks (64, 128, 256 channels), 96 / 112 -> four (.., 512);
+// every block is conv3x3 + BN + ReLU, conv3x3 stride 2 + BN + ReLU; the level-1 maps join after block 0
 struct PhaseNetPart {
   int cin0 = 24;                          // phase channels = nbands * num_phase
-  ConvLayer conv[6];                      // conv_net.{0,1,2}.{0,3}
+  int size = 48;                          // level-0 map edge; level-1 maps are size / 2
+  int n_blocks = 3;
+  ConvLayer conv[8];                      // conv_net.{0..3}.{0,3}
   LinearLayer fc0, fc4, cls;
   bool has_cls = false;
   int chunk = 1024;                       // windows per convolution pass
@@ -117,25 +120,31 @@ static int mlp_run(const MlpPart& P, const float* x, int M, float* out, int ldo,
   return MIMAMO_OK;
 }
 
-static int phasenet_init(const TensorTable& T, const std::string& pre, int cin0, PhaseNetPart& P) {
+static int phasenet_init(const TensorTable& T, const std::string& pre, int cin0, PhaseNetPart& P, int size = 48) {
   MM_REQUIRE(cin0 >= 1 && cin0 <= 64, MIMAMO_E_RUNTIME, "PhaseNet supports 1..64 phase channels (2*num_phase), got %d", cin0);
+  MM_REQUIRE(size == 48 || size == 96 || size == 112, MIMAMO_E_VALUE, "Incorrect input size");      // reference :31-32
   P.cin0 = cin0;
+  P.size = size;
+  P.n_blocks = size == 48 ? 3 : 4;
   { const char* e = getenv("MIMAMO_HEAD_CHUNK"); if (e && atoi(e) > 0) P.chunk = atoi(e); }
-  const int chans[3][2] = {{cin0, 64}, {cin0 + 64, 128}, {128, 256}};
+  if (size != 48 && P.chunk > 256) P.chunk = 256;              // 4-5x the activations per window
   int rc = MIMAMO_OK;
-  for (int b = 0; b < 3 && !rc; ++b) {
+  for (int b = 0; b < P.n_blocks && !rc; ++b) {
+    const int cout = 64 << b, cin = b == 0 ? cin0 : (b == 1 ? cin0 + 64 : 64 << (b - 1));
     const std::string blk = pre + "conv_net." + std::to_string(b) + ".";
-    rc = make_phase_conv(T, blk + "0", blk + "1", chans[b][1], chans[b][0], 1, P.conv[2 * b]);
-    if (!rc) rc = make_phase_conv(T, blk + "3", blk + "4", chans[b][1], chans[b][1], 2, P.conv[2 * b + 1]);
+    rc = make_phase_conv(T, blk + "0", blk + "1", cout, cin, 1, P.conv[2 * b]);
+    if (!rc) rc = make_phase_conv(T, blk + "3", blk + "4", cout, cout, 2, P.conv[2 * b + 1]);
   }
   {
     const char* e = getenv("MIMAMO_HEAD_CALIB");
     if (!(e && e[0] == '0')) {
-      const int relu_in[6] = {0, 64, 64, 128, 128, 256};     // post-ReLU input channels of conv_net.{0,1,2}.{0,3}
-      for (int i = 1; i < 6 && !rc; ++i) rc = compensate_phase_conv(P.conv[i], relu_in[i]);
+      // post-ReLU input channels of conv_net.{b}.{0,3}: all of them except the phase inputs (block 0's first conv, and
+      // the level-1 channels [64, 64 + cin0) of the skip concatenation read by block 1's first conv)
+      for (int i = 1; i < 2 * P.n_blocks && !rc; ++i) rc = compensate_phase_conv(P.conv[i], i == 2 ? 64 : P.conv[i].Cin);
     }
   }
-  if (!rc) rc = make_linear(T, pre + "fc.0", pre + "fc.2", 256, 256, 1, false, P.fc0);
+  const int last = 64 << (P.n_blocks - 1);
+  if (!rc) rc = make_linear(T, pre + "fc.0", pre + "fc.2", 256, last, 1, false, P.fc0);
   if (!rc) rc = make_linear(T, pre + "fc.4", pre + "fc.6", 256, 256, 1, false, P.fc4);
   if (!rc && T.find(pre + "classifier.0.weight")) {            // Linear(256, 1) + BatchNorm1d(1, eps=1e-6) (reference :62-64)
     rc = make_linear(T, pre + "classifier.0", pre + "classifier.1", 1, 256, 0, true, P.cls, 1e-6f);
@@ -149,28 +158,30 @@ static void phasenet_free(PhaseNetPart& P) {
 }
 
 namespace {
-struct PhaseNetLayout { size_t pool, fc, a0, a1, cat, a2, a3, a4, a5, total; };
+struct PhaseNetLayout { size_t pool, fc, a0, mid[8], total; };       // mid[i]: output of conv[i] (mid[1] doubles as the skip concat)
+// spatial edge of conv[i]'s output, its channel pitch
+inline int pn_edge(const PhaseNetPart& P, int i) { return P.size >> ((i + 1) / 2); }
+inline int pn_pitch(const PhaseNetPart& P, int i) { return i == 1 ? 128 : P.conv[i].Cout; }
 PhaseNetLayout phasenet_layout(const PhaseNetPart& P, int M) {
   PhaseNetLayout L;
   size_t cur = 0;
   auto take = [&](size_t bytes) { size_t at = cur; cur += align_up(bytes, 1024); return at; };
   const size_t Mc = (size_t)(M < P.chunk ? M : P.chunk);
-  L.pool = take((size_t)M * 256 * 4);
+  const int last = 64 << (P.n_blocks - 1);
+  L.pool = take((size_t)M * last * 4);
   L.fc = take((size_t)M * 256 * 4);
-  L.a0 = take(Mc * 48 * 48 * 64 * 2);     // phase_0 as NHWC (cin0 -> 64 channels)
-  L.a1 = take(Mc * 48 * 48 * 64 * 2);     // conv_net[0][0]
-  L.cat = take(Mc * 24 * 24 * 128 * 2);   // [conv_net[0][3] (64) | phase_1 (cin0) | zero pad]
-  L.a2 = take(Mc * 24 * 24 * 128 * 2);    // conv_net[1][0]
-  L.a3 = take(Mc * 12 * 12 * 128 * 2);    // conv_net[1][3]
-  L.a4 = take(Mc * 12 * 12 * 256 * 2);    // conv_net[2][0]
-  L.a5 = take(Mc * 6 * 6 * 256 * 2);      // conv_net[2][3]
+  L.a0 = take(Mc * P.size * P.size * 64 * 2);                // phase_0 as NHWC (cin0 -> 64 channels)
+  for (int i = 0; i < 2 * P.n_blocks; ++i) {
+    const size_t e = (size_t)pn_edge(P, i);
+    L.mid[i] = take(Mc * e * e * pn_pitch(P, i) * 2);        // mid[1] = [conv_net[0][3] (64) | phase_1 (cin0) | zero pad] at pitch 128
+  }
   L.total = cur;
   return L;
 }
 }  // namespace
 
-// phase_0 f32[M,cin0,48,48], phase_1 f32[M,cin0,24,24] -> out[m][0..256) at pitch ldo (the `feature=True` output).
-// Alternatively (a0_nhwc != nullptr) the inputs arrive as the phase tail writes them for this net: a0_nhwc f16
+// phase_0 f32[M,cin0,S,S], phase_1 f32[M,cin0,S/2,S/2] -> out[m][0..256) at pitch ldo (the `feature=True` output).
+// Alternatively (a0_nhwc != nullptr, S = 48) the inputs arrive as the phase tail writes them for this net: a0_nhwc f16
 // [M][48][48][a0_pitch] holding the cin0 level-0 channels, cat_nhwc f16 [M][24][24][128] holding the level-1 channels at
 // [64, 64 + cin0) and zeros above (channels [0,64) are overwritten here by conv_net[0][3]).
 static int phasenet_run(const PhaseNetPart& P, const float* phase_0, const float* phase_1, int M, float* out, int ldo,
@@ -178,28 +189,29 @@ static int phasenet_run(const PhaseNetPart& P, const float* phase_0, const float
   const PhaseNetLayout L = phasenet_layout(P, M);
   float* pool = (float*)(ws + L.pool);
   float* fc = (float*)(ws + L.fc);
-  const int c0 = P.cin0;
+  const int c0 = P.cin0, S = P.size, S1 = P.size / 2, nc = 2 * P.n_blocks, last = 64 << (P.n_blocks - 1);
   int rc = MIMAMO_OK;
   for (int m0 = 0; m0 < M && !rc; m0 += P.chunk) {
     const int Mc = M - m0 < P.chunk ? M - m0 : P.chunk;
-    void* a0 = ws + L.a0; void* a1 = ws + L.a1; void* cat = ws + L.cat; void* a2 = ws + L.a2;
-    void* a3 = ws + L.a3; void* a4 = ws + L.a4; void* a5 = ws + L.a5;
+    void* a0 = ws + L.a0;
+    void* mid[8];
+    for (int i = 0; i < nc; ++i) mid[i] = ws + L.mid[i];
     if (a0_nhwc) {
-      cat = cat_nhwc + (size_t)m0 * 24 * 24 * 128;
-      rc = conv_forward(P.conv[0], a0_nhwc + (size_t)m0 * 48 * 48 * a0_pitch, Mc, 48, 48, a1, 64, nullptr, 0, s, a0_pitch, c0);
+      mid[1] = cat_nhwc + (size_t)m0 * S1 * S1 * 128;
+      rc = conv_forward(P.conv[0], a0_nhwc + (size_t)m0 * S * S * a0_pitch, Mc, S, S, mid[0], 64, nullptr, 0, s, a0_pitch, c0);
     } else {
-      rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * 48 * 48, Mc, c0, 48, 48, a0, 64, 0, 64, kHeadElem, s);
-      if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * 24 * 24, Mc, c0, 24, 24, cat, 128, 64, 64, kHeadElem, s);
-      if (!rc) rc = conv_forward(P.conv[0], a0, Mc, 48, 48, a1, 64, nullptr, 0, s);
+      rc = nchw_to_nhwc16(phase_0 + (size_t)m0 * c0 * S * S, Mc, c0, S, S, a0, 64, 0, 64, kHeadElem, s);
+      if (!rc) rc = nchw_to_nhwc16(phase_1 + (size_t)m0 * c0 * S1 * S1, Mc, c0, S1, S1, mid[1], 128, 64, 64, kHeadElem, s);
+      if (!rc) rc = conv_forward(P.conv[0], a0, Mc, S, S, mid[0], 64, nullptr, 0, s);
     }
-    if (!rc) rc = conv_forward(P.conv[1], a1, Mc, 48, 48, cat, 128, nullptr, 0, s);      // -> cat[..., 0:64], 24x24
-    if (!rc) rc = conv_forward(P.conv[2], cat, Mc, 24, 24, a2, 128, nullptr, 0, s);
-    if (!rc) rc = conv_forward(P.conv[3], a2, Mc, 24, 24, a3, 128, nullptr, 0, s);       // 12x12
-    if (!rc) rc = conv_forward(P.conv[4], a3, Mc, 12, 12, a4, 256, nullptr, 0, s);
-    if (!rc) rc = conv_forward(P.conv[5], a4, Mc, 12, 12, a5, 256, nullptr, 0, s);       // 6x6
-    if (!rc) rc = avgpool_to_f32(a5, Mc, 36, 256, pool + (size_t)m0 * 256, 256, 0, kHeadElem, s);
+    for (int i = 1; i < nc && !rc; ++i) {                      // conv[1] writes channels [0,64) of the skip concat (pitch 128)
+      const int e_in = pn_edge(P, i - 1);
+      rc = conv_forward(P.conv[i], mid[i - 1], Mc, e_in, e_in, mid[i], pn_pitch(P, i), nullptr, 0, s);
+    }
+    const int e_out = pn_edge(P, nc - 1);
+    if (!rc) rc = avgpool_to_f32(mid[nc - 1], Mc, e_out * e_out, last, pool + (size_t)m0 * last, last, 0, kHeadElem, s);
   }
-  if (!rc) rc = linear_forward(P.fc0, pool, 256, M, fc, 256, s);
+  if (!rc) rc = linear_forward(P.fc0, pool, last, M, fc, 256, s);
   if (!rc) rc = linear_forward(P.fc4, fc, 256, M, out, ldo, s);
   return rc;
 }
@@ -347,12 +359,12 @@ extern "C" int mimamo_mlp_forward(const mimamo_mlp* m, const float* x, int32_t r
 }
 
 extern "C" void mimamo_phasenet_destroy(mimamo_phasenet* n) { if (n) { phasenet_free(n->p); delete n; } }
-extern "C" int mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t num_channels,
+extern "C" int mimamo_phasenet_create(const mimamo_tensor_desc* tensors, int32_t n_tensors, int32_t input_size, int32_t num_channels,
                                       mimamo_phasenet** out) {
   MM_REQUIRE(tensors && out && n_tensors > 0, MIMAMO_E_VALUE, "null argument");
   TensorTable T{tensors, n_tensors};
   mimamo_phasenet* n = new mimamo_phasenet();
-  const int rc = phasenet_init(T, "", num_channels, n->p);
+  const int rc = phasenet_init(T, "", num_channels, n->p, input_size);
   if (rc) { mimamo_phasenet_destroy(n); return rc; }
   *out = n;
   return MIMAMO_OK;

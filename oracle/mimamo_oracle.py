@@ -408,7 +408,7 @@ def mlp_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, prefix: str = "mlp
 
 def phasenet_forward(sd: Dict[str, torch.Tensor], l0: torch.Tensor, l1: torch.Tensor, prefix: str = "phasenet.",
                      feature: bool = True) -> torch.Tensor:
-    """PhaseNet.forward in eval mode for 48x48 inputs, api/mimamo_net.py:79-95: (rows,C,48,48), (rows,C,24,24) ->
+    """PhaseNet.forward in eval mode, api/mimamo_net.py:79-95: (rows,C,S,S), (rows,C,S/2,S/2) with S in {48, 96, 112} ->
     (rows,256) when `feature`, else (rows,1) after the classifier Linear(256,1) + BatchNorm1d(1, eps=1e-6) (:62-64)."""
     def conv_block(t, blk, stride2):
         p = prefix + "conv_net.%d." % blk
@@ -417,7 +417,10 @@ def phasenet_forward(sd: Dict[str, torch.Tensor], l0: torch.Tensor, l1: torch.Te
                           sd, p + "4"))
 
     t = torch.cat([conv_block(l0, 0, 2), l1], dim=1)
-    t = conv_block(conv_block(t, 1, 2), 2, 2)
+    blk = 1
+    while prefix + "conv_net.%d.0.weight" % blk in sd:                          # 2 more blocks for 48x48 inputs, 3 for 96 / 112 (:33-40)
+        t = conv_block(t, blk, 2)
+        blk += 1
     t = F.avg_pool2d(t, kernel_size=t.shape[-1]).reshape(l0.shape[0], -1)
     for lin, bn in ((0, 2), (4, 6)):                                            # fc: Linear, ReLU, BN, Dropout
         t = _bn(F.relu(F.linear(t, sd[prefix + "fc.%d.weight" % lin], sd[prefix + "fc.%d.bias" % lin])),

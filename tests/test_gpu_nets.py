@@ -193,6 +193,17 @@ def test_mlp_and_phasenet_on_their_own(cuda):
         err = (got - ref).abs().max().item()
         print("PhaseNet feature=%s: max|err| %.2e (scale %.2f)" % (feature, err, ref.abs().max().item()))
         assert got.shape == ref.shape and err < 2e-3 * max(1.0, ref.abs().max().item())
+    for size in (96, 112):                                      # the four-block variants (api/mimamo_net.py:33-40)
+        net = PhaseNet(size, 24, hidden_units=[256, 256, 1], dropout=0.3, feature=True).eval()
+        sd = O.synthetic_state_dict([(k, tuple(v.shape)) for k, v in net.state_dict().items()], seed=5)
+        net.load_state_dict(sd)
+        p0 = torch.randn(1, 3, 24, size, size, generator=gen)
+        p1 = torch.randn(1, 3, 24, size // 2, size // 2, generator=gen)
+        got = net(p0.to(cuda), p1.to(cuda)).cpu()
+        ref = O.phasenet_forward(sd, p0.reshape(3, 24, size, size), p1.reshape(3, 24, size // 2, size // 2), prefix="", feature=True)
+        err = (got - ref).abs().max().item()
+        print("PhaseNet(%d): max|err| %.2e (scale %.2f)" % (size, err, ref.abs().max().item()))
+        assert got.shape == (3, 256) and err < 2e-3 * max(1.0, ref.abs().max().item())
     with pytest.raises(ValueError):
         PhaseNet(50, 24)                                        # "Incorrect input size"
 

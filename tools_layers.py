@@ -22,7 +22,7 @@ for path in sys.argv[1:]:
     passes = max(1, (len(vals) - 12) // n)                       # ResNet passes per step (2048 / images per pass)
     B = 2048 // passes
     chunk = [sum(vals[c * n + i] for c in range(passes)) / passes * (512.0 / B) for i in range(n)]      # per 512 images
-    print("== %s: %d launches; ResNet chunk of %d images: %.0f us measured, %.0f us floor (sum of per-layer max(tensor, HBM))" % (path, len(vals), B, sum(chunk), sum(floors)))
+    print("== %s: %d launches per step, %d-image ResNet passes; per 512 images: %.0f us measured, %.0f us floor (sum of per-layer max(tensor, HBM))" % (path, len(vals), B, sum(chunk), sum(floors)))
     for nm, v, f in zip(names, chunk, floors):
         print("  %-12s %7.1f us  floor %6.1f  (%.0f%%)" % (nm, v, f, 100 * f / v))
     rest = vals[passes * n:]
