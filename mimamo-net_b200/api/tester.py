@@ -386,9 +386,32 @@ class Tester(object):
                 idx = self._window_index[key]
                 streams = self._phase_streams(pre.gray(frames), idx)
                 feats = self.resnet50_extractor.features_from_crops(frames, pre)
-                for v, o, k in zip(group, offs, range(i, j)):
-                    n = v.shape[0]
+                # Head.  The GRU recurs over the snippets of ONE video's batch and treats the frames as independent batch
+                # rows (api/mimamo_net.py:119,138-139), so videos of equal length whose snippets form a single DataLoader batch
+                # can share a forward: their frames simply become more GRU batch rows -- (S snippets, V*L frames).  Nothing in
+                # the head couples rows, so this is bit-identical to one forward per video.
+                g = 0
+                while g < len(group):
+                    n = group[g].shape[0]
                     ranges = snippet_ranges(n, self.length, self.stride)
+                    h = g + 1
+                    if len(ranges) <= self.batch_size:
+                        while h < len(group) and group[h].shape[0] == n and (h - g) < 32:
+                            h += 1
+                    V = h - g
+                    if V > 1:
+                        L = ranges[0][1] - ranges[0][0]
+                        base = torch.tensor([[offs[g + v] + s for v in range(V)] for s, _ in ranges], device=device)      # (S, V)
+                        rows = (base[:, :, None] + torch.arange(L, device=device)[None, None, :]).reshape(-1)
+                        pred = self._head(streams, rows, feats, len(ranges), V * L).view(len(ranges), V, L, -1)
+                        for v in range(V):
+                            pred_v = torch.zeros((n, len(self.label_name)), dtype=torch.float32, device=device)
+                            for q, (s0, e0) in enumerate(ranges):                 # in order: the tail snippet overwrites its overlap
+                                pred_v[s0:e0] = pred[q, v]
+                            out[i + g + v] = pred_v
+                        g = h
+                        continue
+                    o = offs[g]
                     pred_v = torch.zeros((n, len(self.label_name)), dtype=torch.float32, device=device)
                     for b0 in range(0, len(ranges), self.batch_size):
                         batch = ranges[b0:b0 + self.batch_size]
@@ -401,7 +424,8 @@ class Tester(object):
                         pred = self._head(streams, rows, feats, len(batch), L)
                         for q, (s, e) in enumerate(batch):
                             pred_v[s:e] = pred[q]
-                    out[k] = pred_v
+                    out[i + g] = pred_v
+                    g += 1
                 i = j
         return out
 

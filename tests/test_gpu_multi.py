@@ -11,7 +11,8 @@ import torch.multiprocessing as mp
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LENGTHS = [150, 64, 300, 70, 13, 129, 300]              # ragged: tail snippets, a short video, uneven shards
+LENGTHS = [150, 64, 300, 300, 70, 13, 129, 300, 150, 150]   # ragged: tail snippets, a short video, uneven shards, runs of equal
+                                                            # lengths (those share a head forward: more GRU batch rows)
 
 
 def _videos():
@@ -26,7 +27,7 @@ def _tester():
     from bench_inputs import synthetic_weights
     from tester import Tester
     resnet_sd, head_sd = synthetic_weights()
-    return Tester(None, batch_size=4, resnet_model=resnet_sd, head_state_dict=head_sd)
+    return Tester(None, batch_size=8, resnet_model=resnet_sd, head_state_dict=head_sd)
 
 
 def _worker(rank, world, port, q):

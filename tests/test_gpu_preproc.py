@@ -127,8 +127,9 @@ def test_video_path_matches_reference_semantics(cuda, n_frames, batch_size):
     assert np.array_equal(frame["clip_a"].to_numpy().astype(np.float32), got.numpy())
     from multi_gpu import run_videos                       # world size 1: the local block is everything
     n2 = max(1, n_frames - 7)
-    both = run_videos(t, [crops, crops[:n2]])
-    assert len(both) == 2 and torch.equal(both[0].cpu(), got) and both[1].shape == (n2, 2)
+    both = run_videos(t, [crops, crops[:n2], crops, crops])  # the two trailing videos share a head forward when one batch holds their snippets
+    assert len(both) == 4 and both[1].shape == (n2, 2)
+    assert torch.equal(both[0].cpu(), got) and torch.equal(both[2].cpu(), got) and torch.equal(both[3].cpu(), got)
     with pytest.raises(ValueError):
         t.predict_frames(torch.zeros(0, 112, 112, 3, dtype=torch.uint8, device=cuda))
 
