@@ -64,6 +64,8 @@ struct ConvParams {
                              // each fetches half of every weight box, multicast into both shared memories (halves the L2->SM weight traffic)
   int store_mode;            // epilogue TMA store granularity: 0 = per warp (32 rows, flat layers), 1 = per column group, 2 = whole tile
   int resident_w;            // halo kernel: the whole 3x3 weight set stays in shared memory (Cin_p == 64, 9 taps <= kBStages boxes)
+  int res_tma;               // residual fetched by TMA straight into the output staging tile (flat 256-wide layers, per-warp stores)
+  alignas(64) CUtensorMap res_map;   // ... through this map: the residual tensor with the geometry of the output map
 };
 
 // ---------------------------------------------------------------------------------------
@@ -248,11 +250,11 @@ struct GemmCfg {
   static constexpr int kEpiBufs = BLOCK_N <= 128 ? 2 : 1;                          // double-buffered staging where shared memory allows
   static constexpr int kEpiBytes = kEpiBufs * kBlockM * BLOCK_N * 2;             // 16-bit [128][BLOCK_N] TMA-store staging
   static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
+  static constexpr int kBudget = 232448 - 1024 - 512 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N;          // double-buffered accumulator (128/256/512)
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 512 + 1024;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
@@ -369,7 +371,8 @@ template <int BLOCK_N, bool BF16, bool HAS_RES, int EPI_BUFS>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
                                                int num_tiles, int tile0, int tile_stride, int m_shift = 0, int m_rank = 0,
-                                               uint32_t tmem_empty_leader = 0 /* cta_group::2: shared::cluster address of the leader's tmem_empty[0] */) {
+                                               uint32_t tmem_empty_leader = 0 /* cta_group::2: shared::cluster address of the leader's tmem_empty[0] */,
+                                               uint64_t* res_bar = nullptr /* [16 warps][2] mbarriers of the TMA residual path */) {
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per tile (64-wide tiles: 2)
@@ -418,8 +421,24 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
     };
+    // Residual by TMA (p.res_tma: flat 256-wide layers with per-warp stores): a warp's 32 x 64 slice of the residual lands,
+    // through a box of the same geometry as its output box, in the very staging slice the warp will store from; each
+    // thread adds its accumulator row to its residual row IN PLACE.  The staging tile and the former cp.async ring form
+    // two such buffers, so the residual of tile i+1 is in flight while tile i is processed.  This removes the per-lane
+    // cp.async address arithmetic from the epilogue (ncu, round 1: these layers issue at 66 % with DRAM at 65-70 %).
+    const bool res_tma = HAS_RES && p.res_tma != 0;
+    const uint64_t map_res = reinterpret_cast<uint64_t>(&p.res_map);
+    auto issue_res_tma = [&](int tile, int buf) {              // lane 0 only
+      const int m_lin = tile / p.n_tiles, n_tile = tile - m_lin * p.n_tiles;
+      const int m_tile = (m_lin << m_shift) + m_rank;
+      const uint32_t bar = smem_u32(&res_bar[ew * 2 + buf]);
+      bar_expect_tx_u32(bar, 32u * ROW_BYTES);
+      tma2d_u32(stage0_u32 + (uint32_t)buf * BUF_BYTES + quarter * (32 * ROW_BYTES), map_res, bar,
+                n_tile * BLOCK_N + half * COLS, m_tile * kBlockM + quarter * 32);
+    };
     int qc = 0;                                               // chunks consumed so far
-    for (int q = 0; q < kResDepth; ++q) issue_residual(q);
+    if (res_tma) { if (lane == 0 && tile0 < num_tiles) issue_res_tma(tile0, 0); }
+    else for (int q = 0; q < kResDepth; ++q) issue_residual(q);
 
     int local = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++local) {
@@ -431,11 +450,20 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       // staging tiles alternate (EPI_BUFS == 2): this one is free once the store issued two tiles ago has read it
-      const uint32_t buf_off = EPI_BUFS == 2 ? (uint32_t)(local & 1) * BUF_BYTES : 0u;
+      const uint32_t buf_off = (EPI_BUFS == 2 || res_tma) ? (uint32_t)(local & 1) * BUF_BYTES : 0u;
       const uint32_t stage_u32 = stage0_u32 + buf_off;
       const uint32_t my_row_u32 = stage_u32 + row * ROW_BYTES;
-      if (issuer) { if (EPI_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
-      sync_store_group();
+      if (res_tma) {
+        if (lane == 0) {
+          tma_store_wait_read();                                 // every store of this warp has read its staging slice
+          if (tile + tile_stride < num_tiles) issue_res_tma(tile + tile_stride, (local & 1) ^ 1);
+        }
+        __syncwarp();
+        mbar_wait(&res_bar[ew * 2 + (local & 1)], (local >> 1) & 1);
+      } else {
+        if (issuer) { if (EPI_BUFS == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+        sync_store_group();
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
       if ((p.debug & 1) && !tmem_empty_leader) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
 #pragma unroll 1
@@ -444,7 +472,12 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
         tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
         tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
         uint32_t rw[16];
-        if (HAS_RES) {
+        if (HAS_RES && res_tma) {                              // this thread's residual row sits where its output row will go
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4 * j]), "=r"(rw[4 * j + 1]), "=r"(rw[4 * j + 2]), "=r"(rw[4 * j + 3])
+                         : "r"(my_row_u32 + (((uint32_t)(c0 / 8 + j) ^ swz) << 4)));
+        } else if (HAS_RES) {
           asm volatile("cp.async.wait_group %0;" ::"n"(kResDepth - 1) : "memory");
           __syncwarp();                                        // every lane's pieces of the chunk have landed
           const uint32_t src = res_u32 + (qc % kResDepth) * 2048 + lane * 64;
@@ -478,7 +511,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_u32 + ((chunk ^ swz) << 4)), "r"(pack2<BF16>(o[0], o[1])),
                        "r"(pack2<BF16>(o[2], o[3])), "r"(pack2<BF16>(o[4], o[5])), "r"(pack2<BF16>(o[6], o[7])) : "memory");
         }
-        if (HAS_RES) {
+        if (HAS_RES && !res_tma) {
           __syncwarp();                                        // all lanes have read the ring slot
           issue_residual(qc + kResDepth);                      // refill it
         }
@@ -515,7 +548,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
         tma_store_commit();
       }
     }
-    if (HAS_RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (HAS_RES && !res_tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (issuer) tma_store_wait_all();
     }
 }
@@ -537,12 +570,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);          // [16 warps][2]: TMA residual path
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (HAS_RES && p.res_tma) {
+      tma_prefetch_desc(&p.res_map);
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    }
     // pair mode: a stage is reusable once BOTH CTAs' MMAs have read it (each CTA's producer also writes the peer's stage)
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], p.pair ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4)); }
@@ -649,7 +687,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0, tile_stride,
-                                                          m_shift, (int)rank);
+                                                          m_shift, (int)rank, 0u, res_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -678,11 +716,11 @@ struct Gemm2Cfg {
   static constexpr int kEpiBufs = 1;
   static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
   static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - kResBytes;
+  static constexpr int kBudget = 232448 - 1024 - 512 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kResBytes + 512 + 1024;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
@@ -703,6 +741,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);          // [16 warps][2]: TMA residual path
   constexpr int kEpiArrivals = 4 * (BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -710,6 +749,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (HAS_RES && p.res_tma) {
+      tma_prefetch_desc(&p.res_map);
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiArrivals); }   // both CTAs' epilogue warps
     fence_barrier_init();
@@ -806,7 +849,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0,
-                                                          tile_stride, 1, (int)rank, mapa_u32(smem_u32(tmem_empty), 0));
+                                                          tile_stride, 1, (int)rank, mapa_u32(smem_u32(tmem_empty), 0), res_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -1696,6 +1739,15 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   p.store_mode = store_mode_setting(0);
   rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr), p.store_mode == 0 ? 32 : kBlockM);
   if (rc) return rc;
+  {
+    // residual through TMA into the staging tile (MIMAMO_RES_TMA=0: the per-lane cp.async ring instead)
+    const char* e = getenv("MIMAMO_RES_TMA");
+    if (residual != nullptr && bn == 256 && p.store_mode == 0 && !(e && e[0] == '0')) {
+      rc = out_map_flat(&p.res_map, L.elem, const_cast<void*>(residual), ld_res, L.Cout, M, bn, 32);
+      if (rc) return rc;
+      p.res_tma = 1;
+    }
+  }
   return launch(L, ma, mb, mo, p, stream);
 }
 
