@@ -1763,7 +1763,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   }
   MM_REQUIRE(ldc % 8 == 0 && (residual == nullptr || ld_res % 8 == 0), MIMAMO_E_VALUE, "row pitches must be multiples of 8");
   if (B == 0) return MIMAMO_OK;
-  const int Ho = out_size(H, L.ksize, L.stride, L.pad), Wo = out_size(W, L.ksize, L.stride, L.pad);
+  int Ho = out_size(H, L.ksize, L.stride, L.pad), Wo = out_size(W, L.ksize, L.stride, L.pad);
   // fill-bound 3x3 layers (Cout <= 128): halo-resident kernel
   if (halo_setting() != 0 && L.ksize == 3 && L.stride == 1 && L.pad == 1 && residual == nullptr && L.block_n <= 128 &&
       W + 2 <= 64) {
@@ -1823,6 +1823,10 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
     const char* e = getenv("MIMAMO_STRIDED_VIEW");
     if (L.ksize == 1 && L.pad == 0 && L.stride > 1 && !(e && e[0] == '0')) {
       vstride = 1; Wv = Wo; Hv = Ho; pix_pitch = (uint64_t)in_pitch * L.stride;
+      // When H is a multiple of the stride the sampled rows of consecutive images are evenly spaced as well, so (row, image)
+      // merge into ONE dimension and a tile's rows may run across images: 14x14 / 7x7 outputs fill 126 of the 128 MMA rows
+      // instead of 98 (9 + 5 row boxes per image).  The dense output tensor merges the same way.
+      if (H == Ho * L.stride && residual == nullptr) { Hv = Ho * B; Ho = Hv; B = 1; }
     }
   }
   // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows

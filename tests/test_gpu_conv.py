@@ -21,6 +21,8 @@ CASES = [
     (2, 56, 56, 256, 128, 1, 2, 0, 1, False),    # strided 1x1: dense boxes over a strided view of the tensor
     (2, 56, 56, 256, 512, 1, 2, 0, 0, False),
     (3, 7, 9, 256, 512, 1, 2, 0, 0, False),      # odd extents: the view ends on the last sampled pixel
+    (5, 14, 14, 512, 256, 1, 2, 0, 1, False),    # even extents: sampled rows merge across images (126-row tiles)
+    (40, 28, 28, 256, 512, 1, 2, 0, 0, False),   # ... with more tiles than one wave of CTA pairs
     (2, 48, 48, 64, 64, 3, 2, 1, 1, False),      # PhaseNet stride-2 3x3
     (3, 12, 12, 256, 256, 3, 2, 1, 1, False),
     (2, 14, 14, 256, 1024, 1, 1, 0, 1, True),    # residual add + ReLU epilogue
