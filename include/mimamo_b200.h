@@ -277,6 +277,15 @@ int mimamo_conv_bf16(const void* x, int32_t B, int32_t H, int32_t W, int32_t Cin
                      int32_t Cout, int32_t ksize, int32_t stride, int32_t pad, int32_t relu,
                      const void* residual, void* out, void* stream);
 
+/* Test hook: two flat 1x1 layers in one launch (conv_chain_kernel; ResNet50 `_increase` + residual + ReLU followed by the
+ * next block's `_reduce` + ReLU, api/resnet50_extractor.py:81).  x bf16 [M,K1], w1 f32 [N1,K1], residual bf16 [M,N1],
+ * w2 f32 [N2,N1]; out1 bf16 [M,N1] = relu(bn1(x w1^T) + residual), out2 bf16 [M,N2] = relu(bn2(out1 w2^T)).
+ * N1 a multiple of 128, N2 in {64, 128}. */
+int mimamo_conv_chain_bf16(const void* x, int32_t M, int32_t K1, const float* w1_host, const float* scale1_host,
+                           const float* shift1_host, int32_t N1, const void* residual, const float* w2_host,
+                           const float* scale2_host, const float* shift2_host, int32_t N2, void* out1, void* out2,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

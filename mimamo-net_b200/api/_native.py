@@ -108,6 +108,8 @@ _SIGNATURES = {
     "mimamo_conv_bf16": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         c_float_p, c_float_p, c_float_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]),
+    "mimamo_conv_chain_bf16": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, c_float_p, c_float_p, c_float_p, ctypes.c_int32,
+                                              vp, c_float_p, c_float_p, c_float_p, ctypes.c_int32, vp, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

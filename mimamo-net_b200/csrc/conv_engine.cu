@@ -244,12 +244,15 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int BLOCK_N, bool HAS_RES>
+// RES: 0 = no residual, 1 = residual through the per-lane cp.async ring (or, p.res_tma, by TMA with the ring's memory as
+// the second staging buffer), 2 = residual by TMA into a SINGLE staging buffer, added in place -- no ring, no second
+// buffer, and the 64 KB they would take go to the operand pipeline (K >= 256 layers: 2 -> 3 stages, cta_group::2: 3 -> 5)
+template <int BLOCK_N, int RES>
 struct GemmCfg {
   static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kEpiBufs = BLOCK_N <= 128 ? 2 : 1;                          // double-buffered staging where shared memory allows
   static constexpr int kEpiBytes = kEpiBufs * kBlockM * BLOCK_N * 2;             // 16-bit [128][BLOCK_N] TMA-store staging
-  static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
+  static constexpr int kResBytes = RES == 1 ? kEpiWarps * kResDepth * 2048 : 0;   // cp.async residual ring
   static constexpr int kBudget = 232448 - 1024 - 512 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -367,12 +370,14 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // written in the same swizzled row layout so that thread = row reads it back conflict-free.  (Pulling the residual
 // of later tiles into L2 first -- TMA prefetch or prefetch.global.L2 -- was measured 10-15 % SLOWER: these layers
 // are bound by bytes through L2, and a prefetch moves every residual byte through it twice.)
-template <int BLOCK_N, bool BF16, bool HAS_RES, int EPI_BUFS>
+template <int BLOCK_N, bool BF16, int RES, int EPI_BUFS>
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, int warp, int lane, uint8_t* sEpi,
                                                uint8_t* sRes, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
                                                int num_tiles, int tile0, int tile_stride, int m_shift = 0, int m_rank = 0,
                                                uint32_t tmem_empty_leader = 0 /* cta_group::2: shared::cluster address of the leader's tmem_empty[0] */,
                                                uint64_t* res_bar = nullptr /* [16 warps][2] mbarriers of the TMA residual path */) {
+    constexpr bool HAS_RES = RES != 0;
+    constexpr bool RES_SINGLE = RES == 2;                     // one staging buffer, residual added in place
     const int ew = warp - 2;
     const int quarter = warp & 3;                             // TMEM lanes [32q, 32q+32) belong to warp%4 == q
     constexpr int PARTS = BLOCK_N / 32 < 4 ? BLOCK_N / 32 : 4;   // column groups per tile (64-wide tiles: 2)
@@ -426,7 +431,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
     // thread adds its accumulator row to its residual row IN PLACE.  The staging tile and the former cp.async ring form
     // two such buffers, so the residual of tile i+1 is in flight while tile i is processed.  This removes the per-lane
     // cp.async address arithmetic from the epilogue (ncu, round 1: these layers issue at 66 % with DRAM at 65-70 %).
-    const bool res_tma = HAS_RES && p.res_tma != 0;
+    const bool res_tma = RES_SINGLE || (HAS_RES && p.res_tma != 0);
     const uint64_t map_res = reinterpret_cast<uint64_t>(&p.res_map);
     auto issue_res_tma = [&](int tile, int buf) {              // lane 0 only
       const int m_lin = tile / p.n_tiles, n_tile = tile - m_lin * p.n_tiles;
@@ -450,10 +455,13 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       // staging tiles alternate (EPI_BUFS == 2): this one is free once the store issued two tiles ago has read it
-      const uint32_t buf_off = (EPI_BUFS == 2 || res_tma) ? (uint32_t)(local & 1) * BUF_BYTES : 0u;
+      const uint32_t buf_off = (EPI_BUFS == 2 || (res_tma && !RES_SINGLE)) ? (uint32_t)(local & 1) * BUF_BYTES : 0u;
       const uint32_t stage_u32 = stage0_u32 + buf_off;
       const uint32_t my_row_u32 = stage_u32 + row * ROW_BYTES;
-      if (res_tma) {
+      if (RES_SINGLE) {
+        mbar_wait(&res_bar[ew * 2], local & 1);                  // this tile's residual slice has landed (it was requested
+                                                                 // once the previous tile's store had read the buffer)
+      } else if (res_tma) {
         if (lane == 0) {
           tma_store_wait_read();                                 // every store of this warp has read its staging slice
           if (tile + tile_stride < num_tiles) issue_res_tma(tile + tile_stride, (local & 1) ^ 1);
@@ -546,6 +554,10 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
           }
         }
         tma_store_commit();
+        if (RES_SINGLE) {                                        // single buffer: the next residual may land once this store has read it
+          tma_store_wait_read();
+          if (tile + tile_stride < num_tiles) issue_res_tma(tile + tile_stride, 0);
+        }
       }
     }
     if (HAS_RES && !res_tma) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -553,11 +565,12 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
     }
 }
 
-template <int BLOCK_N, bool BF16, bool HAS_RES>
+template <int BLOCK_N, bool BF16, int RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
-  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
+  using Cfg = GemmCfg<BLOCK_N, RES>;
+  constexpr bool HAS_RES = RES != 0;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -577,7 +590,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    if (HAS_RES && p.res_tma) {
+    if (RES == 2 || (HAS_RES && p.res_tma)) {
       tma_prefetch_desc(&p.res_map);
       for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     }
@@ -686,8 +699,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0, tile_stride,
-                                                          m_shift, (int)rank, 0u, res_bar);
+    epilogue_warps<BLOCK_N, BF16, RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0, tile_stride,
+                                                      m_shift, (int)rank, 0u, res_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -710,12 +723,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // epilogue warps (each CTA reads its own TMEM lanes); only the leader's MMA warp issues, and its tcgen05.commit is
 // multicast to both CTAs' empty / tmem_full barriers; both epilogues arrive at the leader's tmem_empty barrier.
 // ---------------------------------------------------------------------------------------
-template <int BLOCK_N, bool HAS_RES>
+template <int BLOCK_N, int RES>
 struct Gemm2Cfg {
   static constexpr int kBStageBytes = (BLOCK_N / 2) * kBlockK * 2;
   static constexpr int kEpiBufs = 1;
   static constexpr int kEpiBytes = kBlockM * BLOCK_N * 2;
-  static constexpr int kResBytes = HAS_RES ? kEpiWarps * kResDepth * 2048 : 0;
+  static constexpr int kResBytes = RES == 1 ? kEpiWarps * kResDepth * 2048 : 0;
   static constexpr int kBudget = 232448 - 1024 - 512 - kEpiBytes - kResBytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -724,11 +737,12 @@ struct Gemm2Cfg {
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
-template <int BLOCK_N, bool BF16, bool HAS_RES>
+template <int BLOCK_N, bool BF16, int RES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
-  using Cfg = Gemm2Cfg<BLOCK_N, HAS_RES>;
+  using Cfg = Gemm2Cfg<BLOCK_N, RES>;
+  constexpr bool HAS_RES = RES != 0;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -749,7 +763,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    if (HAS_RES && p.res_tma) {
+    if (RES == 2 || (HAS_RES && p.res_tma)) {
       tma_prefetch_desc(&p.res_map);
       for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     }
@@ -848,8 +862,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, HAS_RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0,
-                                                          tile_stride, 1, (int)rank, mapa_u32(smem_u32(tmem_empty), 0), res_bar);
+    epilogue_warps<BLOCK_N, BF16, RES, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, sRes, tmem_full, tmem_empty, tmem_base, num_tiles, tile0,
+                                                      tile_stride, 1, (int)rank, mapa_u32(smem_u32(tmem_empty), 0), res_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -1016,7 +1030,377 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    epilogue_warps<BLOCK_N, BF16, false, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles, blockIdx.x, gridDim.x);
+    epilogue_warps<BLOCK_N, BF16, 0, Cfg::kEpiBufs>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, num_tiles, blockIdx.x, gridDim.x);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_chain_kernel: two flat 1x1 layers in ONE persistent launch -- a layer with residual add (ResNet50's
+// `_increase`) and the stride-1 layer that consumes its output (`_reduce` of the next bottleneck block).
+//
+// Executed layer by layer, stages 2-3 of ResNet50 are HBM-bound and the next block's `_reduce` re-reads from HBM the
+// very tensor `_increase` has just written (a quarter of all bytes a stage-2 block moves).  Here every CTA, after the
+// epilogue has stored the [128 pixels][N1] rows of an M tile, runs the second GEMM on exactly those rows: the producer
+// warp waits until the tile's TMA stores have completed (an mbarrier the storing lanes arrive at once
+// cp.async.bulk.wait_group -- completion, not .read -- has covered the store's bulk group), then streams the tile
+// back through the same operand ring.  The rows were written microseconds earlier by this SM, so the loads hit in L2
+// (ncu: DRAM reads of the launch = first layer's activations + residual only) and the second layer's activation read
+// never reaches HBM; no shared memory is needed beyond a staging tile for the second layer's (narrow) output.
+// The sequence is software pipelined by kChainLag M tiles --
+//     main(m0), main(m1), main(m2), chain(m0), main(m3), chain(m1), ...
+// -- so that the stores of a tile have two tile times to land before they are read back, and all three roles (producer,
+// MMA issuer, epilogue) walk the same sub-tile sequence; accumulators alternate between two TMEM buffers per sub-tile.
+// BN = 128-wide sub-tiles with THREE staging tiles: the residual slices of the next two sub-tiles land (by TMA) in the
+// other two while the current one is processed -- with one-deep prefetch every warp's sub-tile period contained a whole
+// HBM load latency (first version: 5.5 us per 128-pixel tile of stage 2 against a 3.6 us HBM floor).
+// ---------------------------------------------------------------------------------------
+constexpr int kChainLag = 2;                 // M tiles between a tile's main sub-tiles and its chained sub-tile
+constexpr int kChainBufs = 3;                // staging / residual landing tiles
+
+struct ChainParams {
+  int m_tiles;
+  int n1_tiles, nkb1;          // main layer: N1 / BN column tiles, K1 / 64 blocks
+  int n2_cols, nkb2;           // chained layer: N2 <= BN output columns, N1 / 64 blocks
+  uint32_t idesc1, idesc2;
+  int relu1, relu2;
+  int debug;                   // timing experiments only (MIMAMO_CHAIN_DEBUG bits): 1 no residual loads, 2 no main stores, 4 no chained stores
+  const float* scale1; const float* shift1;
+  const float* scale2; const float* shift2;
+  alignas(64) CUtensorMap a1;  // main activations  [M][K1], box 64 x 128
+  alignas(64) CUtensorMap b1;  // main weights      [N1][K1], box 64 x BN
+  alignas(64) CUtensorMap out1;// main output       [M][N1], store box (BN/4) x 32
+  alignas(64) CUtensorMap res; // residual          [M][N1], same box
+  alignas(64) CUtensorMap a2;  // main output as the chained layer's activations, box 64 x 128
+  alignas(64) CUtensorMap b2;  // chained weights   [N2][N1], box 64 x N2
+  alignas(64) CUtensorMap out2;// chained output    [M][N2], store box (BN/4) x 32
+};
+
+// RW (resident weights): both weight matrices (<= 64 KB together, K1 = 64, N2 <= 64: ResNet50 stage 2) are loaded once and
+// stay in shared memory; the ring then carries activation boxes only, and the main layer's column sub-tiles share ONE
+// activation load.  The chained launch is bound by bytes through the L2 <-> SM fabric (~65 GB/s per SM in + out, measured on
+// both stage-2 and stage-3 shapes); re-streaming the weights for every 128-pixel tile was 64 of the 304 KB a stage-2 tile moved.
+template <int BN, bool RW>
+struct ChainCfg {
+  static constexpr int kBStageBytes = RW ? 0 : BN * kBlockK * 2;
+  static constexpr int kResidentBytes = RW ? 65536 : 0;
+  static constexpr int kEpiBytes = kChainBufs * kBlockM * BN * 2;        // staging / residual landing tiles
+  static constexpr int kEpi2Bytes = kBlockM * (RW ? 64 : BN) * 2;        // chained layer's output staging (N2 <= BN; RW: N2 <= 64)
+  static constexpr int kBudget = 232448 - 1024 - 1024 - kEpiBytes - kEpi2Bytes - kResidentBytes;
+  static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kResidentBytes + kEpiBytes + kEpi2Bytes + 1024 + 1024;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_done2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
+
+template <int BN, bool BF16, bool RW>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_chain_kernel(const __grid_constant__ ChainParams p) {
+  using Cfg = ChainCfg<BN, RW>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kAStageBytes;
+  uint8_t* sW = sB + STAGES * Cfg::kBStageBytes;             // RW: [N1][64] main weights, then nkb2 boxes [N2][64] of the chained layer
+  uint8_t* sEpi = sW + Cfg::kResidentBytes;
+  uint8_t* sEpi2 = sEpi + Cfg::kEpiBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi2 + Cfg::kEpi2Bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* stored = tmem_empty + 2;                         // [4]: the main output rows of M tile ordinal s (s & 3) are in global memory
+  uint64_t* res_bar = stored + 4;                            // [16 warps][kChainBufs]
+  uint64_t* wfull = res_bar + kChainBufs * kEpiWarps;        // RW: the resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n1 = p.n1_tiles, nkb1 = p.nkb1, nkb2 = p.nkb2;
+  const uint32_t w1_bytes = (uint32_t)n1 * BN * (kBlockK * 2), w2_box_bytes = (uint32_t)p.n2_cols * (kBlockK * 2);
+  const int J = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA (grid <= m_tiles)
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.a1); tma_prefetch_desc(&p.b1); tma_prefetch_desc(&p.out1); tma_prefetch_desc(&p.res);
+    tma_prefetch_desc(&p.a2); tma_prefetch_desc(&p.b2); tma_prefetch_desc(&p.out2);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < 4; ++i) mbar_init(&stored[i], (uint32_t)(kEpiWarps * n1));   // every epilogue warp stores a slice of every main sub-tile
+    for (int i = 0; i < kChainBufs * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    const bool leader = elect_one();
+    const uint32_t tx1 = (uint32_t)kAStageBytes + (uint32_t)Cfg::kBStageBytes;
+    const uint32_t tx2 = (uint32_t)kAStageBytes + (RW ? 0u : w2_box_bytes);
+    const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t stored0 = smem_u32(stored);
+    const uint64_t mapA1 = reinterpret_cast<uint64_t>(&p.a1), mapB1 = reinterpret_cast<uint64_t>(&p.b1);
+    const uint64_t mapA2 = reinterpret_cast<uint64_t>(&p.a2), mapB2 = reinterpret_cast<uint64_t>(&p.b2);
+    int stage = 0; uint32_t parity = 1;
+    uint32_t dA = sA0, dB = sB0, fb = full0, eb = empty0;
+    auto load = [&](uint64_t mapA, uint64_t mapB, int kcol, int arow, int brow, uint32_t tx) {
+      bar_wait_u32(eb, parity);
+      if (leader) {
+        bar_expect_tx_u32(fb, tx);
+        tma2d_u32(dA, mapA, fb, kcol, arow);
+        if (!RW) tma2d_u32(dB, mapB, fb, kcol, brow);
+      }
+      if (++stage == STAGES) { stage = 0; parity ^= 1; dA = sA0; dB = sB0; fb = full0; eb = empty0; }
+      else { dA += kAStageBytes; dB += Cfg::kBStageBytes; fb += 8; eb += 8; }
+    };
+    if (RW && leader) {                                       // both weight matrices, once
+      const uint32_t wb = smem_u32(wfull), sW0 = smem_u32(sW);
+      bar_expect_tx_u32(wb, w1_bytes + (uint32_t)nkb2 * w2_box_bytes);
+      for (int n = 0; n < n1; ++n) tma2d_u32(sW0 + (uint32_t)n * BN * (kBlockK * 2), mapB1, wb, 0, n * BN);
+      for (int kb = 0; kb < nkb2; ++kb) tma2d_u32(sW0 + w1_bytes + (uint32_t)kb * w2_box_bytes, mapB2, wb, kb * kBlockK, 0);
+    }
+#pragma unroll 1
+    for (int s = 0; s < J + kChainLag; ++s) {
+      if (s < J) {
+        const int arow = ((int)blockIdx.x + s * (int)gridDim.x) * kBlockM;
+        if (RW) {
+          load(mapA1, mapB1, 0, arow, 0, tx1);                 // K1 = 64: one activation box serves every column sub-tile
+        } else {
+#pragma unroll 1
+          for (int n = 0; n < n1; ++n)
+#pragma unroll 1
+            for (int kb = 0; kb < nkb1; ++kb) load(mapA1, mapB1, kb * kBlockK, arow, n * BN, tx1);
+        }
+      }
+      if (s >= kChainLag) {
+        const int c = s - kChainLag;
+        const int arow = ((int)blockIdx.x + c * (int)gridDim.x) * kBlockM;
+        bar_wait_u32(stored0 + (c & 3) * 8, (c >> 2) & 1);     // the tile's rows are in global memory (L2)
+        fence_proxy_async_all();                               // generic-proxy acquire -> async-proxy (TMA) reads
+#pragma unroll 1
+        for (int kb = 0; kb < nkb2; ++kb) load(mapA2, mapB2, kb * kBlockK, arow, 0, tx2);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    int stage = 0; uint32_t parity = 0;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0, fb = full0, eb = empty0;
+    int t = 0;                                               // sub-tile counter (TMEM buffer = t & 1)
+    const uint32_t w1_lo = desc_lo(smem_u32(sW)), w2_lo = desc_lo(smem_u32(sW) + w1_bytes);
+    auto advance = [&]() {
+      if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
+      else { a_lo += kAStageBytes >> 4; b_lo += Cfg::kBStageBytes >> 4; fb += 8; eb += 8; }
+    };
+    // one sub-tile whose operands come through the ring (RW: only the activations; weights box kb at w_lo + kb * w_step)
+    auto subtile = [&](int nkb, uint32_t idesc, uint32_t w_lo, uint32_t w_step) {
+      const uint32_t acc = t & 1;
+      bar_wait_u32(tempty0 + acc * 8, ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        bar_wait_u32(fb, parity);
+        tc_fence_after();
+        if (leader) {
+          umma_kblock(d_tmem, a_lo, RW ? w_lo + (uint32_t)kb * w_step : b_lo, idesc, kb != 0 ? 1u : 0u);
+          commit_u32(eb);
+          if (kb == nkb - 1) commit_u32(tfull0 + acc * 8);
+        }
+        advance();
+      }
+      ++t;
+    };
+    if (RW) bar_wait_u32(smem_u32(wfull), 0);
+#pragma unroll 1
+    for (int s = 0; s < J + kChainLag; ++s) {
+      if (s < J) {
+        if (RW) {                                              // every column sub-tile reads the same activation stage
+          bar_wait_u32(fb, parity);
+#pragma unroll 1
+          for (int n = 0; n < n1; ++n, ++t) {
+            const uint32_t acc = t & 1;
+            bar_wait_u32(tempty0 + acc * 8, ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (leader) {
+              umma_kblock(tmem_base + acc * BN, a_lo, w1_lo + (uint32_t)n * (BN * (kBlockK * 2) >> 4), p.idesc1, 0u);
+              commit_u32(tfull0 + acc * 8);
+              if (n == n1 - 1) commit_u32(eb);
+            }
+          }
+          advance();
+        } else {
+#pragma unroll 1
+          for (int n = 0; n < n1; ++n) subtile(nkb1, p.idesc1, 0u, 0u);
+        }
+      }
+      if (s >= kChainLag) subtile(nkb2, p.idesc2, w2_lo, w2_box_bytes >> 4);
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    constexpr int COLS = BN / 4;                              // columns per column group: 32 (SWIZZLE_64B rows) or 64 (SWIZZLE_128B)
+    constexpr int ROW_BYTES = COLS * 2;
+    constexpr int BUF_BYTES = kBlockM * BN * 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t stage0_u32 = smem_u32(sEpi + half * (128 * ROW_BYTES));
+    const uint32_t stage2_u32 = smem_u32(sEpi2 + half * (128 * ROW_BYTES));
+    const uint32_t swz = ROW_BYTES == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+    const uint64_t map_out1 = reinterpret_cast<uint64_t>(&p.out1), map_out2 = reinterpret_cast<uint64_t>(&p.out2);
+    const uint64_t map_res = reinterpret_cast<uint64_t>(&p.res);
+    const int total_main = J * n1;
+    int t = 0, q = 0;                                        // sub-tile counter, main sub-tile counter
+    int buf = 0;                                             // q % kChainBufs
+    uint32_t res_parity = 0;                                 // (q / kChainBufs) & 1
+    // lane 0: M tile ordinals (-1: not a main store) of the last two committed store groups, oldest first.  A main store is
+    // signalled two commits later, when cp.async.bulk.wait_group 2 covers it without stalling.
+    int pend0 = -1, pend1 = -1;
+    auto issue_res = [&](int qq, int b) {                    // lane 0: this warp's 32 x COLS residual slice of main sub-tile qq
+      const int s = qq / n1, n = qq - s * n1;
+      const int m_tile = (int)blockIdx.x + s * (int)gridDim.x;
+      const uint32_t bar = smem_u32(&res_bar[ew * kChainBufs + b]);
+      bar_expect_tx_u32(bar, 32u * ROW_BYTES);
+      tma2d_u32(stage0_u32 + (uint32_t)b * BUF_BYTES + quarter * (32 * ROW_BYTES), map_res, bar, n * BN + half * COLS,
+                m_tile * kBlockM + quarter * 32);
+    };
+    auto committed = [&](int ordinal) {                      // lane 0, after tma_store_commit() of a group (ordinal >= 0: a main store)
+      if (pend0 >= 0) {
+        tma_store_wait_done2();                              // complete (not just read): everything but the two newest groups
+        mbar_arrive(&stored[pend0 & 3]);
+      }
+      pend0 = pend1; pend1 = ordinal;
+    };
+    auto flush = [&]() {                                     // lane 0: no later commit will signal the pending main stores
+      if (pend0 >= 0 || pend1 >= 0) {
+        tma_store_wait_all();
+        if (pend0 >= 0) mbar_arrive(&stored[pend0 & 3]);
+        if (pend1 >= 0) mbar_arrive(&stored[pend1 & 3]);
+        pend0 = pend1 = -1;
+      }
+    };
+    // accumulator row -> scale/shift (+ residual from the staging row) -> ReLU -> 16-bit row in the staging tile
+    auto drain = [&](uint32_t taddr, uint32_t my_row_u32, const float* scale, const float* shift, int relu, bool has_res) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+        uint32_t rw[16];
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4 * j]), "=r"(rw[4 * j + 1]), "=r"(rw[4 * j + 2]), "=r"(rw[4 * j + 3])
+                         : "r"(my_row_u32 + (((uint32_t)(c0 / 8 + j) ^ swz) << 4)));
+        }
+        tmem_ld_wait();
+        const float4* sc = reinterpret_cast<const float4*>(scale + c0);
+        const float4* sh = reinterpret_cast<const float4*>(shift + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 s0 = __ldg(sc + 2 * g), s1 = __ldg(sc + 2 * g + 1), t0 = __ldg(sh + 2 * g), t1 = __ldg(sh + 2 * g + 1);
+          float o[8] = {__uint_as_float(v[8 * g]) * s0.x + t0.x, __uint_as_float(v[8 * g + 1]) * s0.y + t0.y,
+                        __uint_as_float(v[8 * g + 2]) * s0.z + t0.z, __uint_as_float(v[8 * g + 3]) * s0.w + t0.w,
+                        __uint_as_float(v[8 * g + 4]) * s1.x + t1.x, __uint_as_float(v[8 * g + 5]) * s1.y + t1.y,
+                        __uint_as_float(v[8 * g + 6]) * s1.z + t1.z, __uint_as_float(v[8 * g + 7]) * s1.w + t1.w};
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<BF16>(rw[4 * g + j]);
+              o[2 * j] += f.x; o[2 * j + 1] += f.y;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          }
+          const uint32_t chunk = (uint32_t)(c0 / 8 + g);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_u32 + ((chunk ^ swz) << 4)), "r"(pack2<BF16>(o[0], o[1])),
+                       "r"(pack2<BF16>(o[2], o[3])), "r"(pack2<BF16>(o[4], o[5])), "r"(pack2<BF16>(o[6], o[7])) : "memory");
+        }
+      }
+    };
+    const bool dbg_nores = (p.debug & 1) != 0, dbg_nostore = (p.debug & 2) != 0, dbg_nostore2 = (p.debug & 4) != 0;
+    if (lane == 0 && !dbg_nores) {
+      for (int i = 0; i < kChainBufs - 1 && i < total_main; ++i) issue_res(i, i);
+    }
+#pragma unroll 1
+    for (int s = 0; s < J + kChainLag; ++s) {
+      if (s < J) {
+        const int m_tile = (int)blockIdx.x + s * (int)gridDim.x;
+#pragma unroll 1
+        for (int n = 0; n < n1; ++n, ++t, ++q) {
+          const int acc = t & 1;
+          mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
+          tc_fence_after();
+          if (!dbg_nores) mbar_wait(&res_bar[ew * kChainBufs + buf], res_parity);
+          const uint32_t stage_u32 = stage0_u32 + (uint32_t)buf * BUF_BYTES;
+          const int n0 = n * BN + half * COLS;
+          drain(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * COLS, stage_u32 + row * ROW_BYTES,
+                p.scale1 + n0, p.shift1 + n0, p.relu1, true);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // the staging tile of sub-tile q - 1 (its store was committed a whole sub-tile ago) takes the residual of q + 2
+            const int nb = buf == 0 ? kChainBufs - 1 : buf - 1;
+            if (q + kChainBufs - 1 < total_main && !dbg_nores) {
+              tma_store_wait_read();
+              issue_res(q + kChainBufs - 1, nb);
+            }
+            if (!dbg_nostore) tma_store_2d(map_out1, stage_u32 + quarter * (32 * ROW_BYTES), n0, m_tile * kBlockM + quarter * 32);
+            tma_store_commit();
+            committed(s);
+            if (q + 1 == total_main) flush();                // nothing follows that is guaranteed to signal them
+          }
+          if (++buf == kChainBufs) { buf = 0; res_parity ^= 1; }
+        }
+      }
+      if (s >= kChainLag) {
+        const int m_tile = (int)blockIdx.x + (s - kChainLag) * (int)gridDim.x;
+        const int acc = t & 1;
+        mbar_wait(&tmem_full[acc], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        if (half * COLS < p.n2_cols) {
+          if (lane == 0) tma_store_wait_read();              // the previous chained store has read this slice
+          __syncwarp();
+          const int n0 = half * COLS;
+          drain(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * COLS, stage2_u32 + row * ROW_BYTES,
+                p.scale2 + n0, p.shift2 + n0, p.relu2, false);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (!dbg_nostore2) tma_store_2d(map_out2, stage2_u32 + quarter * (32 * ROW_BYTES), n0, m_tile * kBlockM + quarter * 32);
+            tma_store_commit();
+            committed(-1);
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        ++t;
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -1190,7 +1574,7 @@ conv1_line_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (!POOL) {
-    epilogue_warps<BLOCK_N, BF16, false, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles, blockIdx.x, gridDim.x);
+    epilogue_warps<BLOCK_N, BF16, 0, 2>(p, &tmOut, warp, lane, sEpi, nullptr, tmem_full, tmem_empty, tmem_base, p.m_tiles, blockIdx.x, gridDim.x);
   } else {
     // ---- fused BN + ReLU + max pool epilogue: all 16 warps, thread = output column dw, 16 channels.  (With 8 warps
     // of 32 channels the epilogue ran at 0.86 us per line against 0.64 us of load + MMA: two warps per scheduler
@@ -1352,12 +1736,12 @@ static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
 
-template <int BLOCK_N, bool BF16, bool HAS_RES>
+template <int BLOCK_N, bool BF16, int RES>
 static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, HAS_RES>;
+  using Cfg = GemmCfg<BLOCK_N, RES>;
   static DeviceOnce attr_set;
   if (attr_set.need()) {
-    MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, BF16, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set.mark();
   }
   const int tiles = p.m_tiles * p.n_tiles;
@@ -1380,7 +1764,7 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
     static std::atomic<int> pairs_cache[64];
     int max_pairs = pairs_cache[current_device() & 63].load(std::memory_order_relaxed);
     if (!max_pairs) {
-      max_pairs = max_pairs_for(conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, Cfg::kSmemBytes);
+      max_pairs = max_pairs_for(conv_gemm_kernel<BLOCK_N, BF16, RES>, Cfg::kSmemBytes);
       pairs_cache[current_device() & 63].store(max_pairs, std::memory_order_relaxed);
     }
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
@@ -1392,9 +1776,9 @@ static int launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, BF16, HAS_RES>, a, b, o, p));
+    MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, BF16, RES>, a, b, o, p));
   } else {
-    conv_gemm_kernel<BLOCK_N, BF16, HAS_RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
+    conv_gemm_kernel<BLOCK_N, BF16, RES><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, o, p);
   }
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
@@ -1421,12 +1805,12 @@ static int max_pairs_for(Kernel kernel, size_t smem_bytes) {
 }
 
 // cta_group::2 launch (256-wide tiles only): clusters of two CTAs, M = 256 instruction descriptor
-template <bool BF16, bool HAS_RES>
+template <bool BF16, int RES>
 static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<256, HAS_RES>;
+  using Cfg = Gemm2Cfg<256, RES>;
   static DeviceOnce attr_set;
   if (attr_set.need()) {
-    MM_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<256, BF16, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<256, BF16, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set.mark();
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1447,7 +1831,7 @@ static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   static std::atomic<int> pairs_cache[64];
   int max_pairs = pairs_cache[current_device() & 63].load(std::memory_order_relaxed);
   if (!max_pairs) {
-    max_pairs = max_pairs_for(conv_gemm2_kernel<256, BF16, HAS_RES>, Cfg::kSmemBytes);
+    max_pairs = max_pairs_for(conv_gemm2_kernel<256, BF16, RES>, Cfg::kSmemBytes);
     pairs_cache[current_device() & 63].store(max_pairs, std::memory_order_relaxed);
   }
   cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)), 1, 1);
@@ -1458,7 +1842,7 @@ static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<256, BF16, HAS_RES>, a, b, o, p));
+  MM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<256, BF16, RES>, a, b, o, p));
   count_launch();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));
   return MIMAMO_OK;
@@ -1466,8 +1850,11 @@ static int launch_cfg2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
 
 template <int BLOCK_N>
 static int launch_n(bool bf, bool res, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
-  if (bf) return res ? launch_cfg<BLOCK_N, true, true>(a, b, o, p, s) : launch_cfg<BLOCK_N, true, false>(a, b, o, p, s);
-  return res ? launch_cfg<BLOCK_N, false, true>(a, b, o, p, s) : launch_cfg<BLOCK_N, false, false>(a, b, o, p, s);
+  if (BLOCK_N == 256 && res && p.res_tma == 2)
+    return bf ? launch_cfg<BLOCK_N == 256 ? 256 : BLOCK_N, true, BLOCK_N == 256 ? 2 : 1>(a, b, o, p, s)
+              : launch_cfg<BLOCK_N == 256 ? 256 : BLOCK_N, false, BLOCK_N == 256 ? 2 : 1>(a, b, o, p, s);
+  if (bf) return res ? launch_cfg<BLOCK_N, true, 1>(a, b, o, p, s) : launch_cfg<BLOCK_N, true, 0>(a, b, o, p, s);
+  return res ? launch_cfg<BLOCK_N, false, 1>(a, b, o, p, s) : launch_cfg<BLOCK_N, false, 0>(a, b, o, p, s);
 }
 
 // BLOCK_N actually launched: residual layers use at most 128 columns (the residual ring takes the
@@ -1511,8 +1898,9 @@ static int store_mode_setting(int kind) {
 static int launch(const ConvLayer& L, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& o, const ConvParams& p, cudaStream_t s) {
   const bool bf = L.elem == kBF16, res = p.residual != nullptr;
   if (p.pair == 2) {
-    if (bf) return res ? launch_cfg2<true, true>(a, b, o, p, s) : launch_cfg2<true, false>(a, b, o, p, s);
-    return res ? launch_cfg2<false, true>(a, b, o, p, s) : launch_cfg2<false, false>(a, b, o, p, s);
+    if (res && p.res_tma == 2) return bf ? launch_cfg2<true, 2>(a, b, o, p, s) : launch_cfg2<false, 2>(a, b, o, p, s);
+    if (bf) return res ? launch_cfg2<true, 1>(a, b, o, p, s) : launch_cfg2<true, 0>(a, b, o, p, s);
+    return res ? launch_cfg2<false, 1>(a, b, o, p, s) : launch_cfg2<false, 0>(a, b, o, p, s);
   }
   switch (effective_block_n(L, res)) {
     case 64:  return launch_n<64>(bf, res, a, b, o, p, s);
@@ -1740,15 +2128,105 @@ int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, c
   rc = out_map_flat(&mo, L.elem, out, ldc, L.Cout, M, effective_block_n(L, residual != nullptr), p.store_mode == 0 ? 32 : kBlockM);
   if (rc) return rc;
   {
-    // residual through TMA into the staging tile (MIMAMO_RES_TMA=0: the per-lane cp.async ring instead)
+    // residual through TMA into the staging tile.  MIMAMO_RES_TMA: 0 = the per-lane cp.async ring instead, 1 = two staging
+    // buffers (the ring's memory is the second), 2 = one buffer + a deeper operand pipeline; default: 2 where a tile has
+    // at least four K blocks (the pipeline depth matters there), 1 otherwise
     const char* e = getenv("MIMAMO_RES_TMA");
-    if (residual != nullptr && bn == 256 && p.store_mode == 0 && !(e && e[0] == '0')) {
+    const int want = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : (p.num_k_blocks >= 4 ? 2 : 1);
+    if (residual != nullptr && bn == 256 && p.store_mode == 0 && want != 0) {
       rc = out_map_flat(&p.res_map, L.elem, const_cast<void*>(residual), ld_res, L.Cout, M, bn, 32);
       if (rc) return rc;
-      p.res_tma = 1;
+      p.res_tma = want;
     }
   }
   return launch(L, ma, mb, mo, p, stream);
+}
+
+// MIMAMO_CHAIN=0 runs the two layers of a chain as separate launches (cross-check / A-B measurements)
+bool chain_enabled() {
+  const char* e = getenv("MIMAMO_CHAIN");
+  return !(e && e[0] == '0');
+}
+
+bool chain_supported(const ConvLayer& L1, const ConvLayer& L2) {
+  return L1.ksize == 1 && L1.stride == 1 && L1.pad == 0 && L2.ksize == 1 && L2.stride == 1 && L2.pad == 0 && L1.elem == L2.elem &&
+         L1.Cout % 128 == 0 && L2.Cin_p == L1.Cout && L2.Cout <= 128 && L2.Cout % 64 == 0;
+}
+
+// out1 = act(L1(a) + residual) [M][L1.Cout] (dense rows) and out2 = act(L2(out1)) [M][L2.Cout] in one launch.
+int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M, void* out1, const void* residual, int ld_res,
+                  void* out2, int ldc2, cudaStream_t stream) {
+  MM_REQUIRE(chain_supported(L1, L2), MIMAMO_E_VALUE, "chain_forward: unsupported layer pair (%d -> %d -> %d)", L1.Cin_p, L1.Cout, L2.Cout);
+  MM_REQUIRE(residual != nullptr && ld_res % 8 == 0 && ldc2 % 8 == 0, MIMAMO_E_VALUE, "chain_forward needs a residual and row pitches that are multiples of 8");
+  if (M == 0) return MIMAMO_OK;
+  constexpr int BN = 128;
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.n1_tiles = L1.Cout / BN; p.nkb1 = L1.Cin_p / kBlockK;
+  p.n2_cols = L2.Cout; p.nkb2 = L2.Cin_p / kBlockK;
+  p.idesc1 = make_idesc(BN, L1.elem); p.idesc2 = make_idesc(L2.Cout, L2.elem);
+  p.relu1 = L1.relu; p.relu2 = L2.relu;
+  p.scale1 = L1.scale_dev; p.shift1 = L1.shift_dev; p.scale2 = L2.scale_dev; p.shift2 = L2.shift_dev;
+  // resident weights where both matrices fit (ResNet50 stage 2: 32 + 32 KB); MIMAMO_CHAIN_RW=0 streams them (A-B measurements)
+  { const char* e = getenv("MIMAMO_CHAIN_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  const char* rwe = getenv("MIMAMO_CHAIN_RW");
+  const bool rw = p.nkb1 == 1 && L2.Cout <= 64 &&
+                  ((size_t)L1.Cout * L1.Cin_p + (size_t)L2.Cout * L2.Cin_p) * 2 <= (size_t)ChainCfg<BN, true>::kResidentBytes &&
+                  !(rwe && rwe[0] == '0');
+  const uint32_t es[2] = {1, 1};
+  const uint32_t abox[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
+  {
+    const uint64_t dims[2] = {(uint64_t)L1.Cin_p, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)L1.Cin_p * 2};
+    int rc = encode_map(&p.a1, L1.elem, 2, a, dims, strides, abox, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)L1.Cout, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)L1.Cout * 2};
+    int rc = encode_map(&p.a2, L1.elem, 2, out1, dims, strides, abox, es);
+    if (rc) return rc;
+  }
+  int rc = weight_map(L1, &p.b1, BN);
+  if (!rc) rc = weight_map(L2, &p.b2, L2.Cout);
+  if (!rc) rc = out_map_flat(&p.out1, L1.elem, out1, L1.Cout, L1.Cout, M, BN, 32);
+  if (!rc) rc = out_map_flat(&p.res, L1.elem, const_cast<void*>(residual), ld_res, L1.Cout, M, BN, 32);
+  if (!rc) rc = out_map_flat(&p.out2, L2.elem, out2, ldc2, L2.Cout, M, BN, 32);
+  if (rc) return rc;
+  const bool bf = L1.elem == kBF16;
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, false>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, false>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, true>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, true>::kSmemBytes));
+    attr_set.mark();
+  }
+  const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_profile) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t a0, a1;
+      MM_CUDA(cudaEventCreate(&a0));
+      MM_CUDA(cudaEventCreate(&a1));
+      g_prof_events.emplace_back(a0, a1);
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    g_prof_flops += 2.0 * (double)p.m_tiles * kBlockM * ((double)L1.Cout * L1.Cin_p + (double)L2.Cout * L2.Cin_p);
+    MM_CUDA(cudaEventRecord(e0, stream));
+  }
+  if (rw) {
+    if (bf) conv_chain_kernel<BN, true, true><<<grid, kGemmThreads, ChainCfg<BN, true>::kSmemBytes, stream>>>(p);
+    else conv_chain_kernel<BN, false, true><<<grid, kGemmThreads, ChainCfg<BN, true>::kSmemBytes, stream>>>(p);
+  } else {
+    if (bf) conv_chain_kernel<BN, true, false><<<grid, kGemmThreads, ChainCfg<BN, false>::kSmemBytes, stream>>>(p);
+    else conv_chain_kernel<BN, false, false><<<grid, kGemmThreads, ChainCfg<BN, false>::kSmemBytes, stream>>>(p);
+  }
+  MM_LAUNCH_OK();
+  if (e1) MM_CUDA(cudaEventRecord(e1, stream));
+  return MIMAMO_OK;
 }
 
 int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* out, int ldc, const void* residual,
@@ -1994,5 +2472,25 @@ extern "C" int mimamo_conv_bf16(const void* x, int32_t B, int32_t H, int32_t W, 
     rc = MIMAMO_E_CUDA;
   }
   conv_layer_free(L);
+  return rc;
+}
+
+// Test hook (include/mimamo_b200.h): increase-with-residual + next reduce through conv_chain_kernel, bf16 rows.
+extern "C" int mimamo_conv_chain_bf16(const void* x, int32_t M, int32_t K1, const float* w1_host, const float* scale1_host,
+                                      const float* shift1_host, int32_t N1, const void* residual, const float* w2_host,
+                                      const float* scale2_host, const float* shift2_host, int32_t N2, void* out1, void* out2,
+                                      void* stream) {
+  MM_REQUIRE(x && w1_host && w2_host && residual && out1 && out2, MIMAMO_E_VALUE, "null argument");
+  MM_REQUIRE(K1 % 64 == 0, MIMAMO_E_VALUE, "test hook needs K1 %% 64 == 0");
+  ConvLayer L1, L2;
+  int rc = conv_layer_init(L1, w1_host, scale1_host, shift1_host, N1, K1, 1, 1, 0, 1, kBF16);
+  if (rc == MIMAMO_OK) rc = conv_layer_init(L2, w2_host, scale2_host, shift2_host, N2, N1, 1, 1, 0, 1, kBF16);
+  if (rc == MIMAMO_OK) rc = chain_forward(L1, L2, x, M, out1, residual, N1, out2, N2, (cudaStream_t)stream);
+  if (rc == MIMAMO_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+    set_error("chain kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = MIMAMO_E_CUDA;
+  }
+  conv_layer_free(L1);
+  conv_layer_free(L2);
   return rc;
 }

@@ -55,6 +55,14 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
 int gemm_forward(const ConvLayer& L, const void* a, int M, void* out, int ldc, const void* residual,
                  int ld_res, cudaStream_t stream);
 
+// Two flat 1x1 layers in one launch (conv_chain_kernel): out1 = act(L1(a) + residual), dense [M][L1.Cout] rows, and
+// out2 = act(L2(out1)), [M][L2.Cout] at pitch ldc2.  L2 reads out1 back through L2 right after the tile was stored, so its
+// activation read never reaches HBM.  chain_supported: both stride-1 1x1, L1.Cout % 128 == 0, L2.Cout <= 128.
+bool chain_enabled();
+bool chain_supported(const ConvLayer& L1, const ConvLayer& L2);
+int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M, void* out1, const void* residual, int ld_res,
+                  void* out2, int ldc2, cudaStream_t stream);
+
 int out_size(int in, int k, int s, int p);
 
 // conv1_7x7_s2 over a space-to-depth'ed input (see nn_kernels: conv1_space_to_depth); L holds the

@@ -34,6 +34,7 @@ struct mimamo_resnet50 {
   ConvLayer conv1_im2col;          // fallback lowering: K = 147 -> 192 GEMM over an im2col buffer
   bool use_im2col = false;         // MIMAMO_CONV1=im2col
   bool fuse_pool = true;           // MIMAMO_CONV1_POOL=0: separate pool1 kernel (cross-check of the fused epilogue)
+  bool chain = true;               // MIMAMO_CHAIN=0: `_increase` and the next `_reduce` as separate launches (stages 2-3 chain them, conv_engine.cuh)
   int calib = 2;                   // MIMAMO_RESNET_CALIB: weight rounding 0 = to nearest, 1 = zero-sum residuals, 2 = mean-compensated against
                                    // channel means measured on a built-in synthetic batch at create time (conv_layer_quantize)
   std::vector<ResBlock> blocks;
@@ -81,6 +82,7 @@ extern "C" int mimamo_resnet50_create(const mimamo_tensor_desc* tensors, int32_t
   net->use_im2col = c1 && strcmp(c1, "im2col") == 0;
   const char* fp = getenv("MIMAMO_CONV1_POOL");
   net->fuse_pool = !(fp && fp[0] == '0');
+  net->chain = chain_enabled();
   const char* cb = getenv("MIMAMO_RESNET_CALIB");
   if (cb && cb[0] >= '0' && cb[0] <= '2') net->calib = cb[0] - '0';
   int rc = make_conv(T, "conv1_7x7_s2", 64, 3, 7, 2, 3, 1, net->elem, net->conv1_im2col, 147);
@@ -201,6 +203,7 @@ static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mi
     uint16_t* cur = X;
     uint16_t* nxt = Y;
     int H = 56;
+    bool chained = false;                                      // this block's `_reduce` was computed by the previous block's chain launch
     for (size_t i = 0; i < net->blocks.size() && !rc; ++i) {
       const ResBlock& blk = net->blocks[i];
       const int Ho = out_size(H, 1, blk.stride, 0);
@@ -208,7 +211,7 @@ static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mi
         rc = cal->measure(&blk.reduce, cur, (long long)Bc * H * H, stream);
         if (!rc && blk.has_proj) cal->mus.emplace_back(&blk.proj, cal->mus.back().second);    // same input tensor
       }
-      if (!rc) rc = conv_forward(blk.reduce, cur, Bc, H, H, T1, blk.mid, nullptr, 0, stream);
+      if (!rc && !chained) rc = conv_forward(blk.reduce, cur, Bc, H, H, T1, blk.mid, nullptr, 0, stream);
       if (!rc && cal) rc = cal->measure(&blk.conv3, T1, (long long)Bc * Ho * Ho, stream);
       if (!rc) rc = conv_forward(blk.conv3, T1, Bc, Ho, Ho, T2, blk.mid, nullptr, 0, stream);
       const uint16_t* res = cur;
@@ -217,7 +220,13 @@ static int resnet50_forward(const mimamo_resnet50* net, const float* x, const mi
         res = SK;
       }
       if (!rc && cal) rc = cal->measure(&blk.increase, T2, (long long)Bc * Ho * Ho, stream);
-      if (!rc) rc = conv_forward(blk.increase, T2, Bc, Ho, Ho, nxt, blk.cout, res, blk.cout, stream);
+      // `_increase` of this block and `_reduce` of the next one in one launch (conv_chain_kernel): the next block then
+      // finds its T1 ready.  T1 is free here: this block's 3x3 has consumed it.
+      chained = !cal && net->chain && i + 1 < net->blocks.size() && net->blocks[i + 1].stride == 1 &&
+                chain_supported(blk.increase, net->blocks[i + 1].reduce);
+      if (!rc && chained)
+        rc = chain_forward(blk.increase, net->blocks[i + 1].reduce, T2, Bc * Ho * Ho, nxt, res, blk.cout, T1, net->blocks[i + 1].mid, stream);
+      else if (!rc) rc = conv_forward(blk.increase, T2, Bc, Ho, Ho, nxt, blk.cout, res, blk.cout, stream);
       uint16_t* t = cur; cur = nxt; nxt = t;
       H = Ho;
     }

@@ -70,3 +70,52 @@ def test_conv_engine(cuda, case, pair, monkeypatch):
     err = (got - ref).abs()
     tol = 2e-2 + 1e-2 * ref.abs()                 # bf16 output rounding (2^-8 relative) + fp32 sum order
     assert (err <= tol).all(), "max err %.4f at ref %.4f" % (err.max().item(), ref.flatten()[err.argmax()].item())
+
+
+CHAIN_CASES = [
+    # M, K1, N1, N2
+    (2 * 56 * 56, 64, 256, 64),        # ResNet50 stage 2: one K block, two 128-wide sub-tiles per M tile, 64-wide chained layer
+    (3 * 28 * 28 + 5, 128, 512, 128),  # stage 3, M not a multiple of 128 (TMA clips the last tile)
+    (100, 64, 128, 64),                # a single partial M tile
+    (300 * 128, 64, 256, 64),          # more M tiles than SMs: the software-pipelined sequence over several tiles per CTA
+    (149 * 128, 128, 512, 128),        # 149 tiles: one CTA owns two M tiles, the others one
+]
+
+
+@pytest.mark.parametrize("rw", ["1", "0"])          # resident weights (stage-2 shapes only) / weights streamed through the ring
+@pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_conv_chain(cuda, case, rw, monkeypatch):
+    """conv_chain_kernel (increase + residual + ReLU, then the next block's reduce + ReLU in one launch) against the two
+    layers computed separately in fp32 on the same bf16-rounded operands (the chained layer reads the bf16-rounded
+    output of the first, exactly like the layer-by-layer path)."""
+    import _native
+    M, K1, N1, N2 = case
+    if rw == "0" and K1 != 64:
+        pytest.skip("only K1 = 64 shapes have a resident-weight variant to switch off")
+    monkeypatch.setenv("MIMAMO_CHAIN_RW", rw)
+    gen = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(M, K1, generator=gen).to(torch.bfloat16)
+    res = torch.randn(M, N1, generator=gen).to(torch.bfloat16)
+    w1 = (torch.randn(N1, K1, generator=gen) * (2.0 / K1) ** 0.5).to(torch.bfloat16).float()
+    w2 = (torch.randn(N2, N1, generator=gen) * (2.0 / N1) ** 0.5).to(torch.bfloat16).float()
+    s1, s2 = (1 + 0.1 * torch.randn(N1, generator=gen)).float(), (1 + 0.1 * torch.randn(N2, generator=gen)).float()
+    t1, t2 = (0.1 * torch.randn(N1, generator=gen)).float(), (0.1 * torch.randn(N2, generator=gen)).float()
+    xd, resd = x.to(cuda), res.to(cuda)
+    out1 = torch.full((M, N1), float("nan"), dtype=torch.bfloat16, device=cuda)
+    out2 = torch.full((M, N2), float("nan"), dtype=torch.bfloat16, device=cuda)
+    arrs = [np.ascontiguousarray(t.numpy()) for t in (w1, s1, t1, w2, s2, t2)]
+    ptr = [_native.f32_host_ptr(a) for a in arrs]
+    rc = _native.lib().mimamo_conv_chain_bf16(_native.dptr(xd), M, K1, ptr[0], ptr[1], ptr[2], N1, _native.dptr(resd),
+                                              ptr[3], ptr[4], ptr[5], N2, _native.dptr(out1), _native.dptr(out2),
+                                              _native.stream_ptr(cuda))
+    _native.check(rc)
+    torch.cuda.synchronize()
+    ref1 = (xd.float() @ w1.to(cuda).t()) * s1.to(cuda) + t1.to(cuda) + resd.float()
+    ref1 = ref1.clamp_min(0)
+    got1 = out1.float()
+    assert torch.isfinite(got1).all() and torch.isfinite(out2.float()).all(), "unwritten / non-finite outputs"
+    err1 = (got1 - ref1).abs()
+    assert (err1 <= 2e-2 + 1e-2 * ref1.abs()).all(), "layer 1: max err %.4f" % err1.max().item()
+    ref2 = ((got1 @ w2.to(cuda).t()) * s2.to(cuda) + t2.to(cuda)).clamp_min(0)       # from the kernel's own 16-bit rows
+    err2 = (out2.float() - ref2).abs()
+    assert (err2 <= 2e-2 + 1e-2 * ref2.abs()).all(), "chained layer: max err %.4f" % err2.max().item()

@@ -66,6 +66,20 @@ def test_weight_rounding_calibration(cuda, monkeypatch):
     assert errs["2"] < 0.6 * errs["0"] and errs["1"] < errs["0"]
 
 
+def test_chained_layers_are_bit_identical(cuda, monkeypatch):
+    """Stages 2-3 run `_increase` (+ residual) and the next block's `_reduce` as one launch (conv_chain_kernel); the chained
+    layer reads the same 16-bit rows the separate launch would read, so pool5 is bit-identical to the layer-by-layer pass."""
+    from resnet50_extractor import Resnet50_Extractor
+    net = O.resnet_synthetic(1)
+    x = _rgb(5, 34).to(cuda)
+    monkeypatch.setenv("MIMAMO_CHAIN", "1")
+    chained = Resnet50_Extractor(model=net).features(x)
+    monkeypatch.setenv("MIMAMO_CHAIN", "0")
+    separate = Resnet50_Extractor(model=net).features(x)
+    assert torch.isfinite(chained).all()
+    assert torch.equal(chained, separate)
+
+
 def test_fused_pool1_is_bit_identical(cuda, monkeypatch):
     """pool1 fused into conv1's epilogue takes the maximum of the same 16-bit values a separate pooling kernel reads."""
     from resnet50_extractor import Resnet50_Extractor
