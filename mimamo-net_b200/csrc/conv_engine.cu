@@ -1081,38 +1081,32 @@ struct ChainParams {
   alignas(64) CUtensorMap out2;// chained output    [M][N2], store box (BN/4) x 32
 };
 
-// RW (resident weights): both weight matrices (<= 64 KB together, K1 = 64, N2 <= 64: ResNet50 stage 2) are loaded once and
-// stay in shared memory; the ring then carries activation boxes only, and the main layer's column sub-tiles share ONE
-// activation load.  The chained launch is bound by bytes through the L2 <-> SM fabric (~65 GB/s per SM in + out, measured on
-// both stage-2 and stage-3 shapes); re-streaming the weights for every 128-pixel tile was 64 of the 304 KB a stage-2 tile moved.
-template <int BN, bool RW>
+template <int BN>
 struct ChainCfg {
-  static constexpr int kBStageBytes = RW ? 0 : BN * kBlockK * 2;
-  static constexpr int kResidentBytes = RW ? 65536 : 0;
+  static constexpr int kBStageBytes = BN * kBlockK * 2;
   static constexpr int kEpiBytes = kChainBufs * kBlockM * BN * 2;        // staging / residual landing tiles
-  static constexpr int kEpi2Bytes = kBlockM * (RW ? 64 : BN) * 2;        // chained layer's output staging (N2 <= BN; RW: N2 <= 64)
-  static constexpr int kBudget = 232448 - 1024 - 1024 - kEpiBytes - kEpi2Bytes - kResidentBytes;
+  static constexpr int kEpi2Bytes = kBlockM * BN * 2;                    // chained layer's output staging (N2 <= BN)
+  static constexpr int kBudget = 232448 - 1024 - 1024 - kEpiBytes - kEpi2Bytes;
   static constexpr int kMaxStages = kBudget / (kAStageBytes + kBStageBytes);
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kResidentBytes + kEpiBytes + kEpi2Bytes + 1024 + 1024;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kEpiBytes + kEpi2Bytes + 1024 + 1024;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_done2() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
 
-template <int BN, bool BF16, bool RW>
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_chain_kernel(const __grid_constant__ ChainParams p) {
-  using Cfg = ChainCfg<BN, RW>;
+  using Cfg = ChainCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kAStageBytes;
-  uint8_t* sW = sB + STAGES * Cfg::kBStageBytes;             // RW: [N1][64] main weights, then nkb2 boxes [N2][64] of the chained layer
-  uint8_t* sEpi = sW + Cfg::kResidentBytes;
+  uint8_t* sEpi = sB + STAGES * Cfg::kBStageBytes;
   uint8_t* sEpi2 = sEpi + Cfg::kEpiBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi2 + Cfg::kEpi2Bytes);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -1120,12 +1114,11 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* stored = tmem_empty + 2;                         // [4]: the main output rows of M tile ordinal s (s & 3) are in global memory
   uint64_t* res_bar = stored + 4;                            // [16 warps][kChainBufs]
-  uint64_t* wfull = res_bar + kChainBufs * kEpiWarps;        // RW: the resident weights have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kChainBufs * kEpiWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n1 = p.n1_tiles, nkb1 = p.nkb1, nkb2 = p.nkb2;
-  const uint32_t w1_bytes = (uint32_t)n1 * BN * (kBlockK * 2), w2_box_bytes = (uint32_t)p.n2_cols * (kBlockK * 2);
+
   const int J = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // M tiles of this CTA (grid <= m_tiles)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.a1); tma_prefetch_desc(&p.b1); tma_prefetch_desc(&p.out1); tma_prefetch_desc(&p.res);
@@ -1134,7 +1127,6 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     for (int i = 0; i < 4; ++i) mbar_init(&stored[i], (uint32_t)(kEpiWarps * n1));   // every epilogue warp stores a slice of every main sub-tile
     for (int i = 0; i < kChainBufs * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
-    mbar_init(wfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -1147,7 +1139,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     // ------------------------------- TMA producer -------------------------------
     const bool leader = elect_one();
     const uint32_t tx1 = (uint32_t)kAStageBytes + (uint32_t)Cfg::kBStageBytes;
-    const uint32_t tx2 = (uint32_t)kAStageBytes + (RW ? 0u : w2_box_bytes);
+    const uint32_t tx2 = (uint32_t)kAStageBytes + (uint32_t)p.n2_cols * (kBlockK * 2);
     const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const uint32_t stored0 = smem_u32(stored);
     const uint64_t mapA1 = reinterpret_cast<uint64_t>(&p.a1), mapB1 = reinterpret_cast<uint64_t>(&p.b1);
@@ -1159,29 +1151,19 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
       if (leader) {
         bar_expect_tx_u32(fb, tx);
         tma2d_u32(dA, mapA, fb, kcol, arow);
-        if (!RW) tma2d_u32(dB, mapB, fb, kcol, brow);
+        tma2d_u32(dB, mapB, fb, kcol, brow);
       }
       if (++stage == STAGES) { stage = 0; parity ^= 1; dA = sA0; dB = sB0; fb = full0; eb = empty0; }
       else { dA += kAStageBytes; dB += Cfg::kBStageBytes; fb += 8; eb += 8; }
     };
-    if (RW && leader) {                                       // both weight matrices, once
-      const uint32_t wb = smem_u32(wfull), sW0 = smem_u32(sW);
-      bar_expect_tx_u32(wb, w1_bytes + (uint32_t)nkb2 * w2_box_bytes);
-      for (int n = 0; n < n1; ++n) tma2d_u32(sW0 + (uint32_t)n * BN * (kBlockK * 2), mapB1, wb, 0, n * BN);
-      for (int kb = 0; kb < nkb2; ++kb) tma2d_u32(sW0 + w1_bytes + (uint32_t)kb * w2_box_bytes, mapB2, wb, kb * kBlockK, 0);
-    }
 #pragma unroll 1
     for (int s = 0; s < J + kChainLag; ++s) {
       if (s < J) {
         const int arow = ((int)blockIdx.x + s * (int)gridDim.x) * kBlockM;
-        if (RW) {
-          load(mapA1, mapB1, 0, arow, 0, tx1);                 // K1 = 64: one activation box serves every column sub-tile
-        } else {
 #pragma unroll 1
-          for (int n = 0; n < n1; ++n)
+        for (int n = 0; n < n1; ++n)
 #pragma unroll 1
-            for (int kb = 0; kb < nkb1; ++kb) load(mapA1, mapB1, kb * kBlockK, arow, n * BN, tx1);
-        }
+          for (int kb = 0; kb < nkb1; ++kb) load(mapA1, mapB1, kb * kBlockK, arow, n * BN, tx1);
       }
       if (s >= kChainLag) {
         const int c = s - kChainLag;
@@ -1201,13 +1183,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
     int stage = 0; uint32_t parity = 0;
     uint32_t a_lo = a_lo0, b_lo = b_lo0, fb = full0, eb = empty0;
     int t = 0;                                               // sub-tile counter (TMEM buffer = t & 1)
-    const uint32_t w1_lo = desc_lo(smem_u32(sW)), w2_lo = desc_lo(smem_u32(sW) + w1_bytes);
-    auto advance = [&]() {
-      if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
-      else { a_lo += kAStageBytes >> 4; b_lo += Cfg::kBStageBytes >> 4; fb += 8; eb += 8; }
-    };
-    // one sub-tile whose operands come through the ring (RW: only the activations; weights box kb at w_lo + kb * w_step)
-    auto subtile = [&](int nkb, uint32_t idesc, uint32_t w_lo, uint32_t w_step) {
+    auto subtile = [&](int nkb, uint32_t idesc) {
       const uint32_t acc = t & 1;
       bar_wait_u32(tempty0 + acc * 8, ((t >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -1217,38 +1193,22 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
         bar_wait_u32(fb, parity);
         tc_fence_after();
         if (leader) {
-          umma_kblock(d_tmem, a_lo, RW ? w_lo + (uint32_t)kb * w_step : b_lo, idesc, kb != 0 ? 1u : 0u);
+          umma_kblock(d_tmem, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
           commit_u32(eb);
           if (kb == nkb - 1) commit_u32(tfull0 + acc * 8);
         }
-        advance();
+        if (++stage == STAGES) { stage = 0; parity ^= 1; a_lo = a_lo0; b_lo = b_lo0; fb = full0; eb = empty0; }
+        else { a_lo += kAStageBytes >> 4; b_lo += Cfg::kBStageBytes >> 4; fb += 8; eb += 8; }
       }
       ++t;
     };
-    if (RW) bar_wait_u32(smem_u32(wfull), 0);
 #pragma unroll 1
     for (int s = 0; s < J + kChainLag; ++s) {
       if (s < J) {
-        if (RW) {                                              // every column sub-tile reads the same activation stage
-          bar_wait_u32(fb, parity);
 #pragma unroll 1
-          for (int n = 0; n < n1; ++n, ++t) {
-            const uint32_t acc = t & 1;
-            bar_wait_u32(tempty0 + acc * 8, ((t >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (leader) {
-              umma_kblock(tmem_base + acc * BN, a_lo, w1_lo + (uint32_t)n * (BN * (kBlockK * 2) >> 4), p.idesc1, 0u);
-              commit_u32(tfull0 + acc * 8);
-              if (n == n1 - 1) commit_u32(eb);
-            }
-          }
-          advance();
-        } else {
-#pragma unroll 1
-          for (int n = 0; n < n1; ++n) subtile(nkb1, p.idesc1, 0u, 0u);
-        }
+        for (int n = 0; n < n1; ++n) subtile(nkb1, p.idesc1);
       }
-      if (s >= kChainLag) subtile(nkb2, p.idesc2, w2_lo, w2_box_bytes >> 4);
+      if (s >= kChainLag) subtile(nkb2, p.idesc2);
     }
   } else {
     // ------------------------------- epilogue warps -------------------------------
@@ -1400,6 +1360,264 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
         ++t;
       }
     }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// conv_chain_smem_kernel: the same two layers with the hand-over ON CHIP (ResNet50 stage 2: K1 = 64, N1 = 256, N2 = 64).
+//
+// Measured on the L2 hand-over above: with the activation tile of the second layer (64 KB per 128 pixels) going back
+// through a 3-stage operand ring behind the first layer's loads, every M tile exposed two load latencies in sequence
+// (3.4 us per tile with all residual loads and stores switched off, against a 3.6 us HBM floor with them on).  Both weight
+// matrices of a stage-2 pair are 32 KB, so here they stay RESIDENT in shared memory, and the epilogue's 16-bit staging
+// tile of a 128-column sub-tile -- two [128 pixels][64 channels] SWIZZLE_128B blocks, which is exactly the K-major
+// operand layout UMMA reads -- is the second layer's A operand: once the epilogue warps have written and fenced a
+// sub-tile, the MMA warp multiplies it by the matching two K blocks of the second layer's weights into a separate TMEM
+// accumulator, while the TMA store of the same tile is in flight.  The ring carries one 16 KB activation box per M tile.
+//
+// Epilogue: the fixed latencies of one sub-tile round (barrier wake-up, tcgen05.ld, the proxy fence, TMA issue) cost a
+// warp ~1.5 us whatever the tile size (measured with every load and store switched off), so the 16 warps form TWO
+// groups of eight that work on alternate sub-tiles -- group = sub-tile parity = TMEM accumulator buffer; a warp owns
+// 32 rows x 64 columns, i.e. whole 128-byte staging rows, and its own residual / store boxes -- and two sub-tiles are
+// always in flight.  Staging tile q & 3 serves sub-tile q: each group rotates through two tiles of its own, the
+// residual of sub-tile q + 2 is requested when the group starts sub-tile q (after the store of q - 2 has read the tile
+// and the chained MMAs on it have retired: tcgen05.commit -> buf_free).  The 64 chained columns of an M tile are drained
+// by the group that finished the tile (32 columns per warp, warp pairs share a staging row and one store).
+// TMEM: 2 x 128 columns (main accumulators, alternating per sub-tile) + 2 x 64 (chained accumulators, per M tile).
+// ---------------------------------------------------------------------------------------
+constexpr int kChainSmemBufs = 4;
+
+struct ChainSmemCfg {
+  static constexpr int BN = 128;
+  static constexpr int N1 = 256;
+  static constexpr int N2 = 64;
+  static constexpr int kWBytes = 65536;                                   // [256][64] + [64][256]
+  static constexpr int kEpiBytes = kChainSmemBufs * kBlockM * BN * 2;
+  static constexpr int kEpi2Bytes = kBlockM * N2 * 2;
+  static constexpr int kTmemCols = 512;                                   // 256 + 128 used; allocations are powers of two
+  static constexpr int kSmemBytes = kAStageBytes + kWBytes + kEpiBytes + kEpi2Bytes + 1024 + 1024;   // ONE activation stage (16 KB per 3.6 us)
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_chain_smem_kernel(const __grid_constant__ ChainParams p) {
+  using Cfg = ChainSmemCfg;
+  constexpr int BN = Cfg::BN, NB = kChainSmemBufs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + kAStageBytes;                           // two boxes [128][64] of the main weights, then four boxes [64][64] of the chained layer
+  uint8_t* sEpi = sW + Cfg::kWBytes;                         // NB x [2 column halves][128 rows][128 B]
+  uint8_t* sEpi2 = sEpi + Cfg::kEpiBytes;                    // [128 rows][128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sEpi2 + Cfg::kEpi2Bytes);
+  uint64_t* empty_bar = full_bar + 1;
+  uint64_t* tmem_full = empty_bar + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* chain_full = tmem_empty + 2;
+  uint64_t* chain_empty = chain_full + 2;
+  uint64_t* staged = chain_empty + 2;                        // [NB]: the eight warps of the group have written (and fenced) the sub-tile in staging tile b
+  uint64_t* buf_free = staged + NB;                          // [NB]: the chained MMAs reading staging tile b have retired
+  uint64_t* res_bar = buf_free + NB;                         // [16 warps][2]
+  uint64_t* wfull = res_bar + 2 * kEpiWarps;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_main = 2 * J;                              // two 128-column sub-tiles per M tile
+  constexpr uint32_t kW1Bytes = Cfg::N1 * kBlockK * 2;       // 32 KB
+  constexpr uint32_t kW2Box = Cfg::N2 * kBlockK * 2;         // 8 KB
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.a1); tma_prefetch_desc(&p.b1); tma_prefetch_desc(&p.out1); tma_prefetch_desc(&p.res);
+    tma_prefetch_desc(&p.b2); tma_prefetch_desc(&p.out2);
+    mbar_init(full_bar, 1); mbar_init(empty_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
+      mbar_init(&chain_full[i], 1); mbar_init(&chain_empty[i], 8);
+    }
+    for (int i = 0; i < NB; ++i) { mbar_init(&staged[i], 8); mbar_init(&buf_free[i], 1); }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_chain = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (elect_one()) {
+      const uint64_t mapA1 = reinterpret_cast<uint64_t>(&p.a1), mapB1 = reinterpret_cast<uint64_t>(&p.b1), mapB2 = reinterpret_cast<uint64_t>(&p.b2);
+      const uint32_t wb = smem_u32(wfull), sW0 = smem_u32(sW);
+      bar_expect_tx_u32(wb, kW1Bytes + 4u * kW2Box);
+      for (int n = 0; n < 2; ++n) tma2d_u32(sW0 + (uint32_t)n * BN * (kBlockK * 2), mapB1, wb, 0, n * BN);
+      for (int kb = 0; kb < 4; ++kb) tma2d_u32(sW0 + kW1Bytes + (uint32_t)kb * kW2Box, mapB2, wb, kb * kBlockK, 0);
+      const uint32_t fb = smem_u32(full_bar), eb = smem_u32(empty_bar);
+#pragma unroll 1
+      for (int c = 0; c < J; ++c) {
+        bar_wait_u32(eb, (uint32_t)(c & 1) ^ 1u);
+        bar_expect_tx_u32(fb, (uint32_t)kAStageBytes);
+        tma2d_u32(smem_u32(sA), mapA1, fb, 0, ((int)blockIdx.x + c * (int)gridDim.x) * kBlockM);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    const uint32_t a_lo = desc_lo(smem_u32(sA)), w1_lo = desc_lo(smem_u32(sW)), w2_lo = desc_lo(smem_u32(sW) + kW1Bytes);
+    const uint32_t e_lo0 = desc_lo(smem_u32(sEpi));
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    const uint32_t cfull0 = smem_u32(chain_full), cempty0 = smem_u32(chain_empty);
+    const uint32_t staged0 = smem_u32(staged), bfree0 = smem_u32(buf_free);
+    // the chained layer's K blocks 2n, 2n + 1 for main sub-tile qq = 2c + n, read from staging tile qq & 3
+    auto chain_part = [&](int qq) {
+      const int c = qq >> 1, n = qq & 1, b = qq & (NB - 1);
+      bar_wait_u32(staged0 + b * 8, (uint32_t)(qq >> 2) & 1u);
+      if (n == 0) bar_wait_u32(cempty0 + (c & 1) * 8, (uint32_t)((c >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d = tmem_chain + (c & 1) * Cfg::N2;
+        const uint32_t e_lo = e_lo0 + (uint32_t)b * (kBlockM * BN * 2 >> 4);
+        umma_kblock(d, e_lo, w2_lo + (uint32_t)(2 * n) * (kW2Box >> 4), p.idesc2, n != 0 ? 1u : 0u);
+        umma_kblock(d, e_lo + (kBlockM * 128 >> 4), w2_lo + (uint32_t)(2 * n + 1) * (kW2Box >> 4), p.idesc2, 1u);
+        commit_u32(bfree0 + b * 8);
+        if (n == 1) commit_u32(cfull0 + (c & 1) * 8);
+      }
+    };
+    bar_wait_u32(smem_u32(wfull), 0);
+#pragma unroll 1
+    for (int q = 0; q < total_main; ++q) {
+      const int c = q >> 1, n = q & 1;
+      if (n == 0) bar_wait_u32(smem_u32(full_bar), (uint32_t)(c & 1));
+      bar_wait_u32(tempty0 + n * 8, (uint32_t)(c & 1) ^ 1u);   // accumulator buffer = q & 1 = n, its use count = c
+      tc_fence_after();
+      if (leader) {
+        umma_kblock(tmem_base + n * BN, a_lo, w1_lo + (uint32_t)n * (BN * (kBlockK * 2) >> 4), p.idesc1, 0u);
+        commit_u32(tfull0 + n * 8);
+        if (n == 1) commit_u32(smem_u32(empty_bar));
+      }
+      if (q >= 1) chain_part(q - 1);
+    }
+    if (total_main > 0) chain_part(total_main - 1);
+  } else {
+    // ------------------------------- epilogue warps -------------------------------
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int g = half & 1;                                  // 64-column half of the sub-tile = one [128 rows][128 B] staging block
+    const int par = half >> 1;                               // group: handles sub-tiles q with q & 1 == par (column sub-tile n = par of every M tile)
+    constexpr int BUF_BYTES = kBlockM * BN * 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t slice0_u32 = smem_u32(sEpi) + g * (kBlockM * 128) + quarter * (32 * 128);   // this warp's 32 x 128 B slice of staging tile 0
+    const uint32_t row0_u32 = smem_u32(sEpi) + g * (kBlockM * 128) + row * 128;
+    const uint64_t map_out1 = reinterpret_cast<uint64_t>(&p.out1), map_out2 = reinterpret_cast<uint64_t>(&p.out2);
+    const uint64_t map_res = reinterpret_cast<uint64_t>(&p.res);
+    const bool dbg_nores = (p.debug & 1) != 0, dbg_nostore = (p.debug & 2) != 0, dbg_nostore2 = (p.debug & 4) != 0;
+    auto issue_res = [&](int qq) {                           // lane 0: this warp's 32 x 64 residual slice of main sub-tile qq (same group)
+      const int b = qq & (NB - 1);
+      const uint32_t bar = smem_u32(&res_bar[ew * 2 + (b >> 1)]);
+      bar_expect_tx_u32(bar, 32u * 128u);
+      tma2d_u32(slice0_u32 + (uint32_t)b * BUF_BYTES, map_res, bar, (qq & 1) * BN + g * 64, ((int)blockIdx.x + (qq >> 1) * (int)gridDim.x) * kBlockM + quarter * 32);
+    };
+    // accumulator row, 32 columns -> scale/shift (+ residual from the staging row) -> ReLU -> 16-bit, into 16-byte chunks chunk0 .. chunk0 + 3 of the row
+    auto drain32 = [&](uint32_t taddr, uint32_t my_row_u32, uint32_t chunk0, const float* scale, const float* shift, int relu, bool has_res) {
+      uint32_t v[32];
+      tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      uint32_t rw[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4 * j]), "=r"(rw[4 * j + 1]), "=r"(rw[4 * j + 2]), "=r"(rw[4 * j + 3])
+                       : "r"(my_row_u32 + (((chunk0 + (uint32_t)j) ^ swz) << 4)));
+      }
+      tmem_ld_wait();
+      const float4* sc = reinterpret_cast<const float4*>(scale);
+      const float4* sh = reinterpret_cast<const float4*>(shift);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 s0 = __ldg(sc + 2 * k), s1 = __ldg(sc + 2 * k + 1), t0 = __ldg(sh + 2 * k), t1 = __ldg(sh + 2 * k + 1);
+        float o[8] = {__uint_as_float(v[8 * k]) * s0.x + t0.x, __uint_as_float(v[8 * k + 1]) * s0.y + t0.y,
+                      __uint_as_float(v[8 * k + 2]) * s0.z + t0.z, __uint_as_float(v[8 * k + 3]) * s0.w + t0.w,
+                      __uint_as_float(v[8 * k + 4]) * s1.x + t1.x, __uint_as_float(v[8 * k + 5]) * s1.y + t1.y,
+                      __uint_as_float(v[8 * k + 6]) * s1.z + t1.z, __uint_as_float(v[8 * k + 7]) * s1.w + t1.w};
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<BF16>(rw[4 * k + j]);
+            o[2 * j] += f.x; o[2 * j + 1] += f.y;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_u32 + (((chunk0 + (uint32_t)k) ^ swz) << 4)), "r"(pack2<BF16>(o[0], o[1])),
+                     "r"(pack2<BF16>(o[2], o[3])), "r"(pack2<BF16>(o[4], o[5])), "r"(pack2<BF16>(o[6], o[7])) : "memory");
+      }
+    };
+    // the 64 chained output columns of M tile ordinal cc: group 1 (it finishes every M tile), 32 columns per warp; the two
+    // warps of a lane quarter share the 128-byte staging rows and one store (64-thread named barrier 1 + quarter)
+    auto chain_epilogue = [&](int cc) {
+      mbar_wait(&chain_full[cc & 1], (uint32_t)((cc >> 1) & 1));
+      tc_fence_after();
+      if (g == 0 && lane == 0) tma_store_wait_read();        // the previous chained store (issued by this lane) has read the rows
+      named_bar_sync(1 + quarter, 64);
+      drain32(tmem_chain + ((uint32_t)(quarter * 32) << 16) + (cc & 1) * Cfg::N2 + g * 32, smem_u32(sEpi2) + row * 128, (uint32_t)(4 * g),
+              p.scale2 + g * 32, p.shift2 + g * 32, p.relu2, false);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&chain_empty[cc & 1]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + quarter, 64);
+      if (g == 0 && lane == 0) {
+        if (!dbg_nostore2) tma_store_2d(map_out2, smem_u32(sEpi2) + quarter * (32 * 128), 0, ((int)blockIdx.x + cc * (int)gridDim.x) * kBlockM + quarter * 32);
+        tma_store_commit();
+      }
+    };
+    if (lane == 0 && !dbg_nores && par < total_main) issue_res(par);
+#pragma unroll 1
+    for (int q = par; q < total_main; q += 2) {
+      const int c = q >> 1, b = q & (NB - 1);
+      if (lane == 0 && !dbg_nores && q + 2 < total_main) {
+        // the group's other staging tile takes the residual of sub-tile q + 2: the store of q - 2 (committed a round ago) must
+        // have read it and the chained MMAs on it must have retired
+        if (q >= 2) {
+          tma_store_wait_read();
+          mbar_wait(&buf_free[b ^ 2], (uint32_t)((q - 2) >> 2) & 1u);
+        }
+        issue_res(q + 2);
+      }
+      if (par == 1 && c >= 1) chain_epilogue(c - 1);         // its MMAs were issued a round ago
+      mbar_wait(&tmem_full[par], (uint32_t)(c & 1));
+      tc_fence_after();
+      if (!dbg_nores) mbar_wait(&res_bar[ew * 2 + (b >> 1)], (uint32_t)(q >> 2) & 1u);
+      const uint32_t my_row_u32 = row0_u32 + (uint32_t)b * BUF_BYTES;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + par * BN + g * 64;
+      const int n0 = par * BN + g * 64;
+      drain32(taddr, my_row_u32, 0u, p.scale1 + n0, p.shift1 + n0, p.relu1, !dbg_nores);
+      drain32(taddr + 32, my_row_u32, 4u, p.scale1 + n0 + 32, p.shift1 + n0 + 32, p.relu1, !dbg_nores);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[par]);
+      fence_proxy_async_smem();                              // generic-proxy writes -> visible to the tensor core and the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&staged[b]);
+        if (!dbg_nostore)
+          tma_store_2d(map_out1, slice0_u32 + (uint32_t)b * BUF_BYTES, n0, ((int)blockIdx.x + c * (int)gridDim.x) * kBlockM + quarter * 32);
+        tma_store_commit();
+      }
+    }
+    if (par == 1 && J > 0) chain_epilogue(J - 1);
     if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
@@ -2168,12 +2386,11 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
   p.idesc1 = make_idesc(BN, L1.elem); p.idesc2 = make_idesc(L2.Cout, L2.elem);
   p.relu1 = L1.relu; p.relu2 = L2.relu;
   p.scale1 = L1.scale_dev; p.shift1 = L1.shift_dev; p.scale2 = L2.scale_dev; p.shift2 = L2.shift_dev;
-  // resident weights where both matrices fit (ResNet50 stage 2: 32 + 32 KB); MIMAMO_CHAIN_RW=0 streams them (A-B measurements)
+  // on-chip hand-over with resident weights where both matrices fit (ResNet50 stage 2: 32 + 32 KB); MIMAMO_CHAIN_SMEM=0 forces
+  // the hand-over through L2 (A-B measurements, cross-check)
   { const char* e = getenv("MIMAMO_CHAIN_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  const char* rwe = getenv("MIMAMO_CHAIN_RW");
-  const bool rw = p.nkb1 == 1 && L2.Cout <= 64 &&
-                  ((size_t)L1.Cout * L1.Cin_p + (size_t)L2.Cout * L2.Cin_p) * 2 <= (size_t)ChainCfg<BN, true>::kResidentBytes &&
-                  !(rwe && rwe[0] == '0');
+  const char* rwe = getenv("MIMAMO_CHAIN_SMEM");
+  const bool rw = p.nkb1 == 1 && L1.Cout == ChainSmemCfg::N1 && L2.Cout == ChainSmemCfg::N2 && !(rwe && rwe[0] == '0');
   const uint32_t es[2] = {1, 1};
   const uint32_t abox[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
   {
@@ -2190,17 +2407,19 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
   }
   int rc = weight_map(L1, &p.b1, BN);
   if (!rc) rc = weight_map(L2, &p.b2, L2.Cout);
-  if (!rc) rc = out_map_flat(&p.out1, L1.elem, out1, L1.Cout, L1.Cout, M, BN, 32);
-  if (!rc) rc = out_map_flat(&p.res, L1.elem, const_cast<void*>(residual), ld_res, L1.Cout, M, BN, 32);
-  if (!rc) rc = out_map_flat(&p.out2, L2.elem, out2, ldc2, L2.Cout, M, BN, 32);
+  // store / residual boxes: 32 rows x 32 columns per warp (L2 hand-over) or x 64 columns per warp pair (on-chip hand-over)
+  const int box_bn = rw ? 256 : BN;
+  if (!rc) rc = out_map_flat(&p.out1, L1.elem, out1, L1.Cout, L1.Cout, M, box_bn, 32);
+  if (!rc) rc = out_map_flat(&p.res, L1.elem, const_cast<void*>(residual), ld_res, L1.Cout, M, box_bn, 32);
+  if (!rc) rc = out_map_flat(&p.out2, L2.elem, out2, ldc2, L2.Cout, M, box_bn, 32);
   if (rc) return rc;
   const bool bf = L1.elem == kBF16;
   static DeviceOnce attr_set;
   if (attr_set.need()) {
-    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, false>::kSmemBytes));
-    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, false>::kSmemBytes));
-    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, true>::kSmemBytes));
-    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN, true>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN>::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmemCfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmemCfg::kSmemBytes));
     attr_set.mark();
   }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
@@ -2218,11 +2437,11 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
     MM_CUDA(cudaEventRecord(e0, stream));
   }
   if (rw) {
-    if (bf) conv_chain_kernel<BN, true, true><<<grid, kGemmThreads, ChainCfg<BN, true>::kSmemBytes, stream>>>(p);
-    else conv_chain_kernel<BN, false, true><<<grid, kGemmThreads, ChainCfg<BN, true>::kSmemBytes, stream>>>(p);
+    if (bf) conv_chain_smem_kernel<true><<<grid, kGemmThreads, ChainSmemCfg::kSmemBytes, stream>>>(p);
+    else conv_chain_smem_kernel<false><<<grid, kGemmThreads, ChainSmemCfg::kSmemBytes, stream>>>(p);
   } else {
-    if (bf) conv_chain_kernel<BN, true, false><<<grid, kGemmThreads, ChainCfg<BN, false>::kSmemBytes, stream>>>(p);
-    else conv_chain_kernel<BN, false, false><<<grid, kGemmThreads, ChainCfg<BN, false>::kSmemBytes, stream>>>(p);
+    if (bf) conv_chain_kernel<BN, true><<<grid, kGemmThreads, ChainCfg<BN>::kSmemBytes, stream>>>(p);
+    else conv_chain_kernel<BN, false><<<grid, kGemmThreads, ChainCfg<BN>::kSmemBytes, stream>>>(p);
   }
   MM_LAUNCH_OK();
   if (e1) MM_CUDA(cudaEventRecord(e1, stream));

@@ -82,7 +82,7 @@ CHAIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("rw", ["1", "0"])          # resident weights (stage-2 shapes only) / weights streamed through the ring
+@pytest.mark.parametrize("rw", ["1", "0"])          # on-chip hand-over with resident weights (K1 = 64, N2 = 64 shapes) / hand-over through L2
 @pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(str(v) for v in c))
 def test_conv_chain(cuda, case, rw, monkeypatch):
     """conv_chain_kernel (increase + residual + ReLU, then the next block's reduce + ReLU in one launch) against the two
@@ -91,8 +91,8 @@ def test_conv_chain(cuda, case, rw, monkeypatch):
     import _native
     M, K1, N1, N2 = case
     if rw == "0" and K1 != 64:
-        pytest.skip("only K1 = 64 shapes have a resident-weight variant to switch off")
-    monkeypatch.setenv("MIMAMO_CHAIN_RW", rw)
+        pytest.skip("only K1 = 64 shapes have an on-chip variant to switch off")
+    monkeypatch.setenv("MIMAMO_CHAIN_SMEM", rw)
     gen = torch.Generator().manual_seed(sum(case))
     x = torch.randn(M, K1, generator=gen).to(torch.bfloat16)
     res = torch.randn(M, N1, generator=gen).to(torch.bfloat16)
