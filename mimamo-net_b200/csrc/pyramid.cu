@@ -31,6 +31,7 @@ struct PlanDev {
   int H, Hp, Kp, nb, n_levels;
   int work_floats;
   int large;            // 1: frame too big for shared memory -> spectrum / intermediates live in a per-CTA global scratch
+  int use_tc;           // large frames: block products as 3xTF32 tcgen05 MMAs (default; MIMAMO_PYR_TC=0: the fp32-FMA block products)
   const float* dct_t;   // [Hp][Kp]
   LevelDev lv[MIMAMO_MAX_LEVELS];
 };
@@ -431,6 +432,417 @@ pyr_build_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ fr
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Large frames on the tensor cores: pyr_build_umma_kernel (tcgen05.mma kind::tf32, 3xTF32 split operands).
+//
+// At 224x224 the dense DCT-domain transform is 1.7 GFLOP per frame and the fp32-FMA block products above reach 29 TFLOP/s.
+// The phase tolerance (1e-4 on an amplitude-weighted phase) needs fp32-class products, so every operand x is split into two
+// TF32 values, hi = tf32(x) and lo = tf32(x - hi) (22 mantissa bits together), and each product is three tensor-core passes
+// accumulated in fp32 in TMEM:  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (lo*lo is below fp32 resolution).
+//   * operands are K-major in global memory in the sense of the FMA kernels (A[k][i], i contiguous), i.e. M/N-contiguous;
+//     UMMA wants K-contiguous rows.  A K chunk of 32 is staged as [128 rows][32 k] SWIZZLE_128B planes (the descriptor format
+//     the convolution engine uses; a 32-float row is one 128-byte swizzle atom row): a staging thread (q = lane & 7,
+//     i4 = 4 * (warp & 7) + lane / 8) takes four float4 (k = 4q .. 4q+3, rows 4 i4 .. 4 i4 + 3), applies the band mask, splits,
+//     and writes four 16-byte vectors (one per row) -- eight lanes with the same rows and q = 0..7 hit eight distinct 16-byte
+//     bank groups of the swizzled row, so the transposing stores are conflict free;
+//   * roles (19 warps): two loader warps bring the raw fp32 chunk global -> shared with cp.async, laid out as the staging
+//     threads' private 16-byte pieces, two chunks deep, completion by cp.async.mbarrier.arrive; sixteen staging warps; one
+//     MMA warp issues 12 UMMA 128 x N x 8 per B operand and chunk, completion by tcgen05.commit -> mbarrier.  Two plane
+//     buffers (one for the two-B outer products); no CTA-wide barrier inside a block product;
+//   * the accumulators (128 lanes x N columns; the outer products compute the real and the imaginary channel of a band
+//     against the same trig rows into two column ranges) are read back with tcgen05.ld, thread = output row.
+// One CTA per SM (224 KB of staging), persistent over the frames; Ct / U live in the per-CTA global scratch as before.
+// Measured (configs[2], 3328 frames of 224x224): stage 216 -> 150 ms.  The block products are NOT tensor-bound (tensor pipe 14 %
+// active): the split planes cost 28 bytes of shared-memory traffic per operand element (raw in/out, hi+lo planes written, each read
+// 1.5x by the three passes), ~1.2 us of the 2.3 us a chunk takes; 63 ms of the 150 are outside the products (phase tail 24,
+// polar conversion + coefficient stores 13).  Next: A operand through TMEM (tcgen05.st, no shared-memory traffic for it) and
+// pre-split table planes fetched by cp.async.bulk.
+// ---------------------------------------------------------------------------------------
+namespace tcg {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {       // bounded spin: a pipeline bug traps instead of hanging the device
+  uint32_t spins = 0, ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 27)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// K-major SWIZZLE_128B matrix descriptor: start address >> 4, LBO = 1 (unused), SBO = 1024 B (8 rows x 128 B), version 1, layout 2
+__device__ __forceinline__ uint64_t desc128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// four K = 8 TF32 UMMAs over one 32-float (128-byte) K chunk: the start address advances by 32 bytes per step
+__device__ __forceinline__ void umma_tf32_k32(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t da = desc128(a_addr + ks * 32), db = desc128(b_addr + ks * 32);
+    const uint32_t acc = ks == 0 ? accumulate : 1u;
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(da), "l"(db),
+        "r"(idesc), "r"(acc) : "memory");
+  }
+}
+// hi part of the TF32 split: x rounded to 10 mantissa bits (round half away from zero in the magnitude bits).  ptxas expands
+// cvt.rna.tf32.f32 into ~10 instructions on sm_100a (the first versions of the staging loop spent most of their issue slots there);
+// this is an add and a mask.  The lo part x - hi is rounded the same way: left as plain fp32 the tensor core would TRUNCATE it,
+// a bias that accumulates linearly over K (measured: coefficient error 2.1e-6 -> 5.7e-6).
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+}  // namespace tcg
+
+constexpr int kUmmaChunk = 32;                               // K per staged chunk: one 128-byte row of TF32
+constexpr int kPlaneBytes = 128 * kUmmaChunk * 4;            // [128 rows][32 k] = 16 KB
+constexpr int kRawSlotBytes = 3 * kPlaneBytes;               // raw fp32 chunk: A, mask | second B, B  (thread-private 16-byte pieces)
+constexpr int kPlaneRegionBytes = 8 * kPlaneBytes;           // single B: 2 buffers x (a_hi, a_lo, b_hi, b_lo); two Bs: 1 buffer x 6 planes
+constexpr int kUmmaSmemBytes = 2 * kRawSlotBytes + kPlaneRegionBytes + 1024 + 256;
+
+struct UmmaCtx {
+  uint8_t* raw;              // [2 slots][3 operands][4 kk][256 thread slots][16 B]: cp.async landing ring, two chunks deep
+  uint8_t* planes;           // 1024-aligned staging planes (see kPlaneRegionBytes)
+  uint64_t* free_bar;        // [2]: the MMAs that read staging buffer b have retired (tcgen05.commit)
+  uint64_t* raw_full;        // [2]: every copy of the chunk in ring slot s has landed (cp.async.mbarrier.arrive by the 64 loader lanes)
+  uint64_t* raw_empty;       // [2]: the 16 staging warps have read ring slot s
+  uint64_t* planes_full;     // [2]: the 16 staging warps have written (and fenced) plane buffer b
+  uint64_t* tmem_free;       // the 16 staging warps have read the previous block's accumulators out of TMEM
+  uint32_t blocks;           // block products started so far (same value in every thread)
+  uint32_t tmem;             // 256 columns: [0,128) first B operand, [128,256) second
+  uint32_t uses[2];          // commits issued on free_bar[b] so far (same value in every thread)
+  uint32_t ring;             // chunks pushed through the raw ring so far (same value in every thread); slot = ring & 1
+  int debug;                 // timing experiments (MIMAMO_PYR_TC=3: no MMAs, 5: no output stores)
+};
+
+constexpr int kStagerThreads = 512;                          // warps 0-15: split / transpose / mask; thread 0 issues the MMAs
+constexpr int kUmmaThreads = kStagerThreads + 96;            // warps 16, 17: cp.async loaders of the A-side and the B-side operands; warp 18: MMA issuer
+
+// The accumulators of one 128 x nj block:  D0[i][j] (+ D1 with B1) = sum_k A[k][i0 + i] * mask * B[k][j0 + j], left in TMEM.
+// Rows beyond M, columns beyond N and k beyond K are staged as zeros.  nj: UMMA N, a multiple of 16 up to 128.
+// Roles: two LOADER warps copy global -> shared (cp.async, 16-byte pieces laid out per staging thread) into a two-chunk ring and
+// signal an mbarrier when a chunk has landed; sixteen STAGING warps (warps 0-7 the A operand and its mask, 8-15 the B operand(s);
+// thread (q = lane & 7, i4 = 4 * (warp & 7) + lane / 8) owns k = 4q .. 4q + 3 of rows 4 i4 .. 4 i4 + 3) turn their pieces into the
+// swizzled K-major hi / lo planes and hand them to the MMA warp through an mbarrier; one elected thread of warp 18 issues the UMMAs.
+// No CTA-wide barrier sits in the chunk loop: the first versions joined all staging threads with __syncthreads every chunk and let
+// one of them issue the MMAs (several hundred serial instructions), which cost 2.8 us per chunk whatever the thread count, the
+// prefetch depth or the way the loads were issued.
+template <bool MASKED, bool DUAL>
+__device__ __forceinline__ void umma_block(UmmaCtx& cx, const float* __restrict__ A, int lda, const float* __restrict__ Mk, int ldm, int M,
+                                           const float* __restrict__ B0, const float* __restrict__ B1, int ldb, int N, int K, int i0, int j0, int nj) {
+  static_assert(!(MASKED && DUAL), "the raw ring has three operand slabs");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (cx.debug & 8) return;                                  // timing experiment: everything but the block products
+  const int nchunks = (K + kUmmaChunk - 1) / kUmmaChunk;
+  const uint32_t block_no = cx.blocks++;
+  if (warp == 18) {
+    // ------------------------------- MMA issuer -------------------------------
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nj >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (block_no > 0) tcg::mbar_wait(cx.tmem_free, (block_no - 1u) & 1u);   // the previous block's accumulators have been read
+    uint32_t buf = 1;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      buf = DUAL ? 0u : (buf ^ 1u);
+      tcg::mbar_wait(&cx.planes_full[buf], cx.uses[buf] & 1u);
+      tcg::fence_after();
+      if (lane == 0 && (cx.debug & 2)) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcg::smem_u32(&cx.free_bar[buf])) : "memory");
+      } else if (lane == 0) {
+        const uint32_t b = tcg::smem_u32(cx.planes + (size_t)buf * 4 * kPlaneBytes);
+        const uint32_t ah = b, al = b + kPlaneBytes, bh = b + 2 * kPlaneBytes, bl = b + 3 * kPlaneBytes;
+        tcg::umma_tf32_k32(cx.tmem, al, bh, idesc, c > 0 ? 1u : 0u);
+        tcg::umma_tf32_k32(cx.tmem, ah, bl, idesc, 1u);
+        tcg::umma_tf32_k32(cx.tmem, ah, bh, idesc, 1u);
+        if (DUAL) {
+          const uint32_t ch = b + 4 * kPlaneBytes, cl = b + 5 * kPlaneBytes;
+          tcg::umma_tf32_k32(cx.tmem + 128, al, ch, idesc, c > 0 ? 1u : 0u);
+          tcg::umma_tf32_k32(cx.tmem + 128, ah, cl, idesc, 1u);
+          tcg::umma_tf32_k32(cx.tmem + 128, ah, ch, idesc, 1u);
+        }
+        tcg::commit(&cx.free_bar[buf]);
+      }
+      __syncwarp();
+      ++cx.uses[buf];
+    }
+    return;
+  }
+  const bool is_b = warp >= 16 ? warp == 17 : warp >= 8;       // which operand side this thread works for
+  const float* G = is_b ? B0 : A;
+  const float* G2 = is_b ? B1 : Mk;
+  const int ld = is_b ? ldb : lda, ld2 = is_b ? ldb : ldm;
+  const int x0 = is_b ? j0 : i0, lim = is_b ? N : M;
+  const bool two = is_b ? DUAL : MASKED;
+  const uint32_t slab0 = tcg::smem_u32(cx.raw) + (is_b ? 2u * kPlaneBytes : 0u);     // slabs: [A][mask | B1][B0]
+  const uint32_t slab2 = tcg::smem_u32(cx.raw) + kPlaneBytes;
+  const int q = lane & 7;
+  if (warp >= 16) {
+    // ------------------------------- loader warp -------------------------------
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c, ++cx.ring) {
+      const uint32_t slot = cx.ring & 1u, so = slot * kRawSlotBytes;
+      if (cx.ring >= 2) tcg::mbar_wait(&cx.raw_empty[slot], ((cx.ring >> 1) - 1u) & 1u);
+#pragma unroll 1
+      for (int s = 0; s < 8; ++s) {                            // the 256 thread slots of this side, 32 per pass
+        const int i4 = s * 4 + (lane >> 3);
+        const int x = x0 + 4 * i4;
+        const bool ok = x < lim && (!is_b || 4 * i4 < nj);
+        const uint32_t dst = (uint32_t)(s * 32 + lane) * 16u + so;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = c * kUmmaChunk + 4 * q + kk;
+          const bool v = ok && k < K;
+          const size_t off = (size_t)(v ? k : 0) * ld + (v ? x : 0);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slab0 + dst + kk * 4096u), "l"(G + off), "r"(v ? 16u : 0u) : "memory");
+          if (two) {
+            const size_t off2 = (size_t)(v ? k : 0) * ld2 + (v ? x : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slab2 + dst + kk * 4096u), "l"(G2 + off2), "r"(v ? 16u : 0u) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tcg::smem_u32(&cx.raw_full[slot])) : "memory");
+    }
+    return;
+  }
+  // ------------------------------- staging warps -------------------------------
+  const int i4 = (warp & 7) * 4 + (lane >> 3);
+  const int tg = threadIdx.x & 255;
+  const uint32_t raw0 = slab0 + tg * 16u, raw2 = slab2 + tg * 16u;
+  auto lds4 = [&](uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+  };
+  // rows 4 i4 + r (r = 0..3) of the [128][32] plane: the four k values of this thread form one 16-byte vector per row
+  auto stage = [&](const float4 (&v)[4], uint8_t* hi_plane, uint8_t* lo_plane) {
+    const float rows[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
+                              {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = 4 * i4 + r;
+      const uint32_t off = (uint32_t)row * 128u + (uint32_t)((q ^ (row & 7)) << 4);
+      uint4 h, l;
+      h.x = tcg::tf32_hi(rows[r][0]); h.y = tcg::tf32_hi(rows[r][1]); h.z = tcg::tf32_hi(rows[r][2]); h.w = tcg::tf32_hi(rows[r][3]);
+      l.x = tcg::tf32_hi(rows[r][0] - __uint_as_float(h.x)); l.y = tcg::tf32_hi(rows[r][1] - __uint_as_float(h.y));
+      l.z = tcg::tf32_hi(rows[r][2] - __uint_as_float(h.z)); l.w = tcg::tf32_hi(rows[r][3] - __uint_as_float(h.w));
+      *reinterpret_cast<uint4*>(hi_plane + off) = h;
+      *reinterpret_cast<uint4*>(lo_plane + off) = l;
+    }
+  };
+  uint32_t buf = 1;
+  for (int c = 0; c < nchunks; ++c, ++cx.ring) {
+    const uint32_t slot = cx.ring & 1u, so = slot * kRawSlotBytes;
+    tcg::mbar_wait(&cx.raw_full[slot], (cx.ring >> 1) & 1u);  // the chunk has landed
+    float4 r1[4], r2[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      r1[kk] = lds4(raw0 + so + kk * 4096u);
+      if (two) r2[kk] = lds4(raw2 + so + kk * 4096u);
+      if (MASKED && !is_b) { r1[kk].x *= r2[kk].x; r1[kk].y *= r2[kk].y; r1[kk].z *= r2[kk].z; r1[kk].w *= r2[kk].w; }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcg::smem_u32(&cx.raw_empty[slot])) : "memory");
+    // single B: two plane buffers alternate; two Bs: one buffer.  Its previous MMAs must have retired before it is overwritten.
+    buf = DUAL ? 0u : (buf ^ 1u);
+    if (cx.uses[buf] > 0) tcg::mbar_wait(&cx.free_bar[buf], (cx.uses[buf] - 1u) & 1u);
+    uint8_t* base = cx.planes + (size_t)buf * 4 * kPlaneBytes;
+    if (!is_b) {
+      stage(r1, base, base + kPlaneBytes);
+    } else {
+      stage(r1, base + 2 * kPlaneBytes, base + 3 * kPlaneBytes);
+      if (DUAL) stage(r2, base + 4 * kPlaneBytes, base + 5 * kPlaneBytes);
+    }
+    tcg::fence_proxy_async_smem();                             // generic-proxy stores -> visible to the tensor core
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcg::smem_u32(&cx.planes_full[buf])) : "memory");
+    ++cx.uses[buf];
+  }
+  tcg::mbar_wait(&cx.free_bar[buf], (cx.uses[buf] - 1u) & 1u);   // every MMA of the block has retired: the accumulators are complete
+  tcg::fence_after();
+}
+
+// block column width for an N-column product: the fewest blocks of at most 128 columns, equal widths rounded up to 16
+__device__ __forceinline__ int umma_bj(int N) {
+  const int nblk = (N + 127) / 128;
+  return (((N + nblk - 1) / nblk) + 15) & ~15;
+}
+
+// C[i][j] = sum_k A[k][i] (* mask) B[k][j] for all i < M, j < N, written to C (leading dimension ldc)
+// (columns [jb, je) only: the band loop below works one block column of the output at a time)
+template <bool MASKED>
+__device__ void umma_product(UmmaCtx& cx, const float* A, int lda, const float* Mk, int ldm, int M, const float* B, int ldb, int N, int K,
+                             float* C, int ldc, int jb, int je) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bj = umma_bj(N);
+  for (int i0 = 0; i0 < M; i0 += 128)
+    for (int j0 = jb; j0 < je; j0 += bj) {
+      umma_block<MASKED, false>(cx, A, lda, Mk, ldm, M, B, nullptr, ldb, N, K, i0, j0, bj);
+      if (warp >= 16) continue;                                // loader warps run ahead into the next block
+      const int i = i0 + 32 * (warp & 3) + lane;              // thread = accumulator row (TMEM lane); warp / 4 selects 32 of the columns
+      const uint32_t taddr = cx.tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+      for (int t0 = 32 * (warp >> 2); t0 < bj && t0 < 32 * (warp >> 2) + 32; t0 += 16) {
+        float v[16];
+        tcg::tmem_ld16(taddr + t0, v);                         // warp-collective: every lane takes part, stores are predicated
+        if (i < M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int j = j0 + t0 + 4 * g;
+            if (j < N) *reinterpret_cast<float4*>(C + (size_t)i * ldc + j) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        }
+      }
+      tcg::fence_before();                                     // the next block's first MMA overwrites the accumulators: the MMA warp
+      __syncwarp();                                            // waits for all sixteen warps
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcg::smem_u32(cx.tmem_free)) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+pyr_build_umma_kernel(const __grid_constant__ PlanDev P, const float* __restrict__ frames, int T, const __grid_constant__ OutPtrs outs,
+                      const int* __restrict__ root, float* scratch, long long n_frames, int polar) {
+  extern __shared__ uint8_t umma_smem_raw[];
+  __shared__ float red[32];
+  __shared__ uint32_t tmem_slot;
+  UmmaCtx cx;
+  cx.planes = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(umma_smem_raw) + 1023) & ~(uintptr_t)1023);
+  cx.raw = cx.planes + kPlaneRegionBytes;
+  cx.free_bar = reinterpret_cast<uint64_t*>(cx.raw + 2 * kRawSlotBytes);
+  cx.raw_full = cx.free_bar + 2;
+  cx.raw_empty = cx.raw_full + 2;
+  cx.planes_full = cx.raw_empty + 2;
+  cx.tmem_free = cx.planes_full + 2;
+  cx.uses[0] = cx.uses[1] = 0;
+  cx.ring = 0;
+  cx.blocks = 0;
+  cx.debug = P.use_tc;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tcg::mbar_init(&cx.free_bar[i], 1);
+      tcg::mbar_init(&cx.raw_full[i], 64);                    // both loader warps' lanes (cp.async.mbarrier.arrive.noinc)
+      tcg::mbar_init(&cx.raw_empty[i], 16);                   // one arrival per staging warp
+      tcg::mbar_init(&cx.planes_full[i], 16);
+    }
+    tcg::mbar_init(cx.tmem_free, 16);
+    tcg::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tcg::tmem_alloc(&tmem_slot, 256);
+  tcg::fence_before();
+  __syncthreads();
+  tcg::fence_after();
+  cx.tmem = tmem_slot;
+  float* Ct = scratch + (size_t)blockIdx.x * ((size_t)P.Kp * P.Kp + P.work_floats);
+  float* W = Ct + (size_t)P.Kp * P.Kp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long n = blockIdx.x; n < n_frames; n += gridDim.x) {
+    if (root != nullptr && root[n] != (int)n) continue;    // duplicate of an earlier frame: its root's coefficients are reused
+    const long long w = n / T;
+    const int t = (int)(n - w * T);
+    const int H = P.H, Hp = P.Hp, Kp = P.Kp;
+    float* Xs = W;
+    float* R1 = W + (size_t)Hp * Hp;
+    const float* frame = frames + (size_t)n * H * H;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+      const int m = i / Hp, nn = i - m * Hp;
+      float v = 0.f;
+      if (m < H && nn < H) v = __ldg(frame + (size_t)m * H + nn);
+      Xs[i] = v;
+      part += v;
+    }
+    const float mean = block_sum(part, red) / (float)(H * H);
+    for (int i = threadIdx.x; i < Hp * Hp; i += blockDim.x) {
+      const int m = i / Hp, nn = i - m * Hp;
+      if (m < H && nn < H) Xs[i] -= mean;
+    }
+    __syncthreads();
+    umma_product<false>(cx, Xs, Hp, nullptr, 0, Hp, P.dct_t, Kp, Kp, Hp, R1, Kp, 0, Kp);       // R1[n][k] = sum_m X[m][n] dct[m][k]
+    __syncthreads();
+    umma_product<false>(cx, P.dct_t, Kp, nullptr, 0, Kp, R1, Kp, Kp, Hp, Ct, Kp, 0, Kp);       // Ct[l][k] = sum_n dct[n][l] R1[n][k]
+    __syncthreads();
+    for (int li = 0; li < P.n_levels; ++li) {
+      const LevelDev& L = P.lv[li];
+      float2* out = reinterpret_cast<float2*>(outs.p[li]);
+      const int c = L.c, hp = L.hp, cp = L.cp;
+      const int bj = umma_bj(cp);
+      // One band and one block column [j0, j0 + bj) of its output at a time: the four inner products fill that column range of
+      // U (both channels, both halves), the outer products consume it at once.  The live part of the per-CTA scratch is then
+      // Ct + half a band of U (~600 KB at 224x224): with a whole band (1 MB x 148 CTAs) the scratch did not fit L2 and the first
+      // version of this kernel moved 88 GB through DRAM per 3328 frames, every chunk waiting on a DRAM-latency load.
+      for (int b = 0; b < P.nb; ++b)
+        for (int j0 = 0; j0 < cp; j0 += bj) {
+          const int je = min(j0 + bj, cp);
+          for (int job = 0; job < 4; ++job) {                  // U[ch][half*hp + k][x], x in [j0, je)
+            const int ch = job >> 1, half = job & 1;
+            const float* mask = L.masks + ((size_t)((b * 2 + ch) * 2 + half) * hp) * hp;
+            const float* tab = L.trig + (size_t)L.inner_sel[ch][half] * hp * cp;
+            umma_product<true>(cx, Ct, Kp, mask, hp, hp, tab, cp, cp, hp, W + ((size_t)ch * 2 * hp + half * hp) * cp, cp, j0, je);
+          }
+          __syncthreads();
+          const float* Bre = W;                                // out_ch[y][x] = sum_kk trig[kk][y] * U_ch[kk][x], both channels per block
+          const float* Bim = Bre + (size_t)2 * hp * cp;
+          for (int i0 = 0; i0 < cp; i0 += 128) {
+            umma_block<false, true>(cx, L.trig, cp, nullptr, 0, cp, Bre, Bim, cp, cp, 2 * hp, i0, j0, bj);
+            if (warp >= 16) continue;                          // loader warps run ahead into the next block
+            const int y = i0 + 32 * (warp & 3) + lane;
+            const uint32_t taddr = cx.tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+            for (int t0 = 32 * (warp >> 2); t0 < bj && t0 < 32 * (warp >> 2) + 32; t0 += 16) {
+              float re[16], im[16];
+              tcg::tmem_ld16(taddr + t0, re);
+              tcg::tmem_ld16(taddr + 128 + t0, im);
+              if (y < c) {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                  const int x = j0 + t0 + g;
+                  if (x >= c) continue;
+                  float2 v = make_float2(re[g], im[g]);
+                  if (polar) {   // (phase, magnitude) exactly as the phase tail computes them from (re, im), once per distinct frame
+                    const float ph = atan2f(v.y, v.x);
+                    const float mg = __fadd_rn(sqrtf(__fadd_rn(__fmul_rn(v.y, v.y), __fmul_rn(v.x, v.x))), 1e-10f);
+                    v = make_float2(ph, mg);
+                  }
+                  if (!(cx.debug & 4)) out[((((size_t)w * P.nb + b) * T + t) * c + y) * (size_t)c + x] = v;
+                }
+              }
+            }
+            tcg::fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcg::smem_u32(cx.tmem_free)) : "memory");
+          }
+          __syncthreads();
+        }
+    }
+  }
+  tcg::fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tcg::fence_after();
+    tcg::tmem_dealloc(cx.tmem, 256);
+  }
+}
+
 }  // namespace mimamo
 
 using namespace mimamo;
@@ -488,6 +900,7 @@ extern "C" int mimamo_pyr_plan_create(int32_t H, int32_t Hp, int32_t Kp, int32_t
   const size_t budget_floats = ((size_t)max_optin - 1024) / sizeof(float);
   size_t work;
   d.large = (ct_floats + need > budget_floats) ? 1 : 0;
+  { const char* e = getenv("MIMAMO_PYR_TC"); d.use_tc = e ? atoi(e) : 1; }
   if (d.large) {
     work = need;                       // one band at a time, buffers in global scratch
   } else {
@@ -563,8 +976,19 @@ int pyr_build_launch(const mimamo_pyr_plan* plan, const float* frames, int64_t n
   if (plan->d.large) {
     const size_t need = pyr_scratch_bytes(plan);
     MM_REQUIRE(workspace && workspace_bytes >= need, MIMAMO_E_VALUE, "workspace too small: need %zu bytes", need);
-    const unsigned grid = (unsigned)(n_frames < plan->large_grid ? n_frames : plan->large_grid);
-    pyr_build_kernel<true><<<grid, kPyrThreads, 0, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames, polar);
+    if (plan->d.use_tc) {
+      static DeviceOnce attr_set;
+      if (attr_set.need()) {
+        MM_CUDA(cudaFuncSetAttribute(pyr_build_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaSmemBytes));
+        attr_set.mark();
+      }
+      const int sms = plan->large_grid / 2;                    // one CTA per SM (192 KB of staging planes)
+      const unsigned grid = (unsigned)(n_frames < sms ? n_frames : sms);
+      pyr_build_umma_kernel<<<grid, kUmmaThreads, kUmmaSmemBytes, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames, polar);
+    } else {
+      const unsigned grid = (unsigned)(n_frames < plan->large_grid ? n_frames : plan->large_grid);
+      pyr_build_kernel<true><<<grid, kPyrThreads, 0, stream>>>(plan->d, frames, T, outs, root, (float*)workspace, n_frames, polar);
+    }
   } else {
     pyr_build_kernel<false><<<(unsigned)n_frames, kPyrThreads, plan->smem_bytes, stream>>>(plan->d, frames, T, outs, root, nullptr, n_frames, polar);
   }
