@@ -484,11 +484,12 @@ def bench_pyramid224(ctx):
                 "d2h_bytes_per_step": world * sum(o.shape[0] * o.shape[1] * o.shape[2] for o in outs) * 4,
                 "note": "frames from pinned host memory; the per-map sums of the phase maps are read back (their consumer, PhaseNet, is on the device)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "pyr_build_kernel + coeff_to_polar_kernel + phase_tail_kernel (whole stage)",
+        "roofline": {"bound": "hbm", "kernel": "pyr_build_umma_kernel (tcgen05 kind::tf32, 3xTF32) + phase_tail_kernel (whole stage)",
                      "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
                      "algorithmic_bytes_per_window": bytes_per_window, "peak_source": src,
                      "note": "algorithmic bytes = 4*T*H^2 in + 4*nb*(T-1)*sum_l (H/2^(l-1))^2 out per window (SURVEY.md section 8(d)); "
-                             "the stage is bound by fp32 arithmetic, not by HBM (DESIGN.md section 3.1)"},
+                             "the stage is bound by the dense transform (1.7 GFLOP per frame as split-TF32 tensor-core products, their "
+                             "shared-memory staging) and the tail's fp32 instruction issue, not by HBM (DESIGN.md section 3.1)"},
         "sliding_windows": {"value": world * W * steps / (ms_clip / 1e3), "unit": UNIT, "ms_per_step": ms_clip / steps,
                             "frac": bytes_per_window * W * steps / (ms_clip / 1e3) / 1e9 / peak,
                             "note": "the same 256 windows taken as sliding windows over 4 clips of 64 frames (what Tester feeds): "

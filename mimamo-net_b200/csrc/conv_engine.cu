@@ -1629,6 +1629,276 @@ conv_chain_smem_kernel(const __grid_constant__ ChainParams p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// conv_chain_stream_kernel: the on-chip hand-over for ResNet50 stage 3 (K1 = 128, N1 = 512, N2 = 128), where the two weight
+// matrices (128 KB each) cannot stay in shared memory.  Same structure as conv_chain_smem_kernel -- staging tile = A operand of
+// the chained GEMM, two alternating epilogue groups, four staging tiles -- with the weights STREAMED through a small ring of
+// [128][64] boxes in the static order the MMA warp consumes them: per 128-column sub-tile q the two K blocks of the main weights,
+// then the two K blocks of the chained weights that belong to sub-tile q - 1.  The M tile's activations (two K blocks, 32 KB) are
+// loaded once and serve its four sub-tiles; the single buffer is enough because the MMA warp runs one to two sub-tiles ahead of
+// the epilogue.  The L2 hand-over moved 800 KB per 128 pixels between L2 and the SM (the ~10 TB/s L2 cap); this one moves 576 KB.
+// TMEM: 2 x 128 columns main + 2 x 128 chained = all 512.
+// ---------------------------------------------------------------------------------------
+struct ChainStreamCfg {
+  static constexpr int BN = 128;
+  static constexpr int N1 = 512, K1 = 128, N2 = 128;
+  static constexpr int kBStages = 2;
+  static constexpr int kBBox = BN * kBlockK * 2;                          // 16 KB
+  static constexpr int kABytes = 2 * kAStageBytes;                        // the M tile's two K blocks
+  static constexpr int kEpiBytes = kChainSmemBufs * kBlockM * BN * 2;
+  static constexpr int kEpi2Bytes = kBlockM * N2 * 2;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kABytes + kBStages * kBBox + kEpiBytes + kEpi2Bytes + 1024 + 1024;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_chain_stream_kernel(const __grid_constant__ ChainParams p) {
+  using Cfg = ChainStreamCfg;
+  constexpr int BN = Cfg::BN, NB = kChainSmemBufs, SB = Cfg::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                        // [2 K blocks][128 rows][128 B]
+  uint8_t* sB = sA + Cfg::kABytes;                           // SB x [128 rows][128 B] weight boxes
+  uint8_t* sEpi = sB + SB * Cfg::kBBox;                      // NB x [2 column halves][128 rows][128 B]
+  uint8_t* sEpi2 = sEpi + Cfg::kEpiBytes;                    // [2 column halves][128 rows][128 B]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sEpi2 + Cfg::kEpi2Bytes);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* b_full = a_empty + 1;
+  uint64_t* b_empty = b_full + SB;
+  uint64_t* tmem_full = b_empty + SB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* chain_full = tmem_empty + 2;
+  uint64_t* chain_empty = chain_full + 2;
+  uint64_t* staged = chain_empty + 2;                        // [NB]
+  uint64_t* buf_free = staged + NB;                          // [NB]
+  uint64_t* res_bar = buf_free + NB;                         // [16 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_main = 4 * J;                              // four 128-column sub-tiles per M tile
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.a1); tma_prefetch_desc(&p.b1); tma_prefetch_desc(&p.out1); tma_prefetch_desc(&p.res);
+    tma_prefetch_desc(&p.b2); tma_prefetch_desc(&p.out2);
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
+      mbar_init(&chain_full[i], 1); mbar_init(&chain_empty[i], 8);
+    }
+    for (int i = 0; i < NB; ++i) { mbar_init(&staged[i], 8); mbar_init(&buf_free[i], 1); }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_chain = tmem_base + 2 * BN;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (elect_one()) {
+      const uint64_t mapA1 = reinterpret_cast<uint64_t>(&p.a1), mapB1 = reinterpret_cast<uint64_t>(&p.b1), mapB2 = reinterpret_cast<uint64_t>(&p.b2);
+      const uint32_t af = smem_u32(a_full), ae = smem_u32(a_empty), sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+      int bs = 0; uint32_t bpar = 1;
+      auto load_b = [&](uint64_t map, int c0, int c1) {
+        bar_wait_u32(smem_u32(&b_empty[bs]), bpar);
+        const uint32_t fb = smem_u32(&b_full[bs]);
+        bar_expect_tx_u32(fb, (uint32_t)Cfg::kBBox);
+        tma2d_u32(sB0 + bs * Cfg::kBBox, map, fb, c0, c1);
+        if (++bs == SB) { bs = 0; bpar ^= 1; }
+      };
+#pragma unroll 1
+      for (int q = 0; q < total_main; ++q) {
+        const int c = q >> 2, n = q & 3;
+        if (n == 0) {                                          // the M tile's activations: both K blocks behind one barrier
+          const int row = ((int)blockIdx.x + c * (int)gridDim.x) * kBlockM;
+          bar_wait_u32(ae, (uint32_t)(c & 1) ^ 1u);
+          bar_expect_tx_u32(af, (uint32_t)Cfg::kABytes);
+          tma2d_u32(sA0, mapA1, af, 0, row);
+          tma2d_u32(sA0 + kAStageBytes, mapA1, af, kBlockK, row);
+        }
+        load_b(mapB1, 0, n * BN);
+        load_b(mapB1, kBlockK, n * BN);
+        if (q >= 1) {                                          // chained weights for the previous sub-tile's 128 channels
+          const int pn = (q - 1) & 3;
+          load_b(mapB2, (2 * pn) * kBlockK, 0);
+          load_b(mapB2, (2 * pn + 1) * kBlockK, 0);
+        }
+      }
+      if (total_main > 0) { load_b(mapB2, 6 * kBlockK, 0); load_b(mapB2, 7 * kBlockK, 0); }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    const bool leader = elect_one();
+    const uint32_t a_lo = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB)), e_lo0 = desc_lo(smem_u32(sEpi));
+    const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
+    const uint32_t cfull0 = smem_u32(chain_full), cempty0 = smem_u32(chain_empty);
+    const uint32_t staged0 = smem_u32(staged), bfree0 = smem_u32(buf_free);
+    const uint32_t bfull0 = smem_u32(b_full), bempty0 = smem_u32(b_empty);
+    int bs = 0; uint32_t bpar = 0;
+    // one K block: A descriptor a, the next weight box of the ring, into accumulator d
+    auto kblock = [&](uint32_t d, uint32_t a, uint32_t idesc, uint32_t accumulate) {
+      bar_wait_u32(bfull0 + bs * 8, bpar);
+      tc_fence_after();
+      if (leader) {
+        umma_kblock(d, a, b_lo0 + (uint32_t)bs * (Cfg::kBBox >> 4), idesc, accumulate);
+        commit_u32(bempty0 + bs * 8);
+      }
+      if (++bs == SB) { bs = 0; bpar ^= 1; }
+    };
+    auto chain_part = [&](int qq) {
+      const int c = qq >> 2, n = qq & 3, b = qq & (NB - 1);
+      bar_wait_u32(staged0 + b * 8, (uint32_t)(qq >> 2) & 1u);
+      if (n == 0) bar_wait_u32(cempty0 + (c & 1) * 8, (uint32_t)((c >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_chain + (c & 1) * Cfg::N2;
+      const uint32_t e_lo = e_lo0 + (uint32_t)b * (kBlockM * BN * 2 >> 4);
+      kblock(d, e_lo, p.idesc2, n != 0 ? 1u : 0u);
+      kblock(d, e_lo + (kBlockM * 128 >> 4), p.idesc2, 1u);
+      if (leader) {
+        commit_u32(bfree0 + b * 8);
+        if (n == 3) commit_u32(cfull0 + (c & 1) * 8);
+      }
+    };
+#pragma unroll 1
+    for (int q = 0; q < total_main; ++q) {
+      const int c = q >> 2, n = q & 3;
+      if (n == 0) bar_wait_u32(smem_u32(a_full), (uint32_t)(c & 1));
+      const uint32_t acc = q & 1;
+      bar_wait_u32(tempty0 + acc * 8, (uint32_t)((q >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      kblock(tmem_base + acc * BN, a_lo, p.idesc1, 0u);
+      kblock(tmem_base + acc * BN, a_lo + (kAStageBytes >> 4), p.idesc1, 1u);
+      if (leader) {
+        commit_u32(tfull0 + acc * 8);
+        if (n == 3) commit_u32(smem_u32(a_empty));
+      }
+      if (q >= 1) chain_part(q - 1);
+    }
+    if (total_main > 0) chain_part(total_main - 1);
+  } else {
+    // ------------------------------- epilogue warps -------------------------------
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    const int g = half & 1;                                  // 64-column half of a sub-tile = one [128 rows][128 B] staging block
+    const int par = half >> 1;                               // group: sub-tiles q with q & 1 == par (column sub-tiles n = par, par + 2)
+    constexpr int BUF_BYTES = kBlockM * BN * 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t slice0_u32 = smem_u32(sEpi) + g * (kBlockM * 128) + quarter * (32 * 128);
+    const uint32_t row0_u32 = smem_u32(sEpi) + g * (kBlockM * 128) + row * 128;
+    const uint32_t slice2_u32 = smem_u32(sEpi2) + g * (kBlockM * 128) + quarter * (32 * 128);
+    const uint32_t row2_u32 = smem_u32(sEpi2) + g * (kBlockM * 128) + row * 128;
+    const uint64_t map_out1 = reinterpret_cast<uint64_t>(&p.out1), map_out2 = reinterpret_cast<uint64_t>(&p.out2);
+    const uint64_t map_res = reinterpret_cast<uint64_t>(&p.res);
+    auto tile_row = [&](int c) { return ((int)blockIdx.x + c * (int)gridDim.x) * kBlockM + quarter * 32; };
+    auto issue_res = [&](int qq) {                           // lane 0: this warp's 32 x 64 residual slice of main sub-tile qq (same group)
+      const int b = qq & (NB - 1);
+      const uint32_t bar = smem_u32(&res_bar[ew * 2 + (b >> 1)]);
+      bar_expect_tx_u32(bar, 32u * 128u);
+      tma2d_u32(slice0_u32 + (uint32_t)b * BUF_BYTES, map_res, bar, (qq & 3) * BN + g * 64, tile_row(qq >> 2));
+    };
+    auto drain32 = [&](uint32_t taddr, uint32_t my_row_u32, uint32_t chunk0, const float* scale, const float* shift, int relu, bool has_res) {
+      uint32_t v[32];
+      tmem_ld16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      tmem_ld16(taddr + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+      uint32_t rw[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rw[4 * j]), "=r"(rw[4 * j + 1]), "=r"(rw[4 * j + 2]), "=r"(rw[4 * j + 3])
+                       : "r"(my_row_u32 + (((chunk0 + (uint32_t)j) ^ swz) << 4)));
+      }
+      tmem_ld_wait();
+      const float4* sc = reinterpret_cast<const float4*>(scale);
+      const float4* sh = reinterpret_cast<const float4*>(shift);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 s0 = __ldg(sc + 2 * k), s1 = __ldg(sc + 2 * k + 1), t0 = __ldg(sh + 2 * k), t1 = __ldg(sh + 2 * k + 1);
+        float o[8] = {__uint_as_float(v[8 * k]) * s0.x + t0.x, __uint_as_float(v[8 * k + 1]) * s0.y + t0.y,
+                      __uint_as_float(v[8 * k + 2]) * s0.z + t0.z, __uint_as_float(v[8 * k + 3]) * s0.w + t0.w,
+                      __uint_as_float(v[8 * k + 4]) * s1.x + t1.x, __uint_as_float(v[8 * k + 5]) * s1.y + t1.y,
+                      __uint_as_float(v[8 * k + 6]) * s1.z + t1.z, __uint_as_float(v[8 * k + 7]) * s1.w + t1.w};
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack2<BF16>(rw[4 * k + j]);
+            o[2 * j] += f.x; o[2 * j + 1] += f.y;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row_u32 + (((chunk0 + (uint32_t)k) ^ swz) << 4)), "r"(pack2<BF16>(o[0], o[1])),
+                     "r"(pack2<BF16>(o[2], o[3])), "r"(pack2<BF16>(o[4], o[5])), "r"(pack2<BF16>(o[6], o[7])) : "memory");
+      }
+    };
+    // the 128 chained output columns of M tile ordinal cc: group 1 (it finishes every M tile), 64 columns (whole staging rows) per warp
+    auto chain_epilogue = [&](int cc) {
+      mbar_wait(&chain_full[cc & 1], (uint32_t)((cc >> 1) & 1));
+      tc_fence_after();
+      if (lane == 0) tma_store_wait_read();                  // this warp's previous chained store has read its slice
+      __syncwarp();
+      const uint32_t taddr = tmem_chain + ((uint32_t)(quarter * 32) << 16) + (cc & 1) * Cfg::N2 + g * 64;
+      drain32(taddr, row2_u32, 0u, p.scale2 + g * 64, p.shift2 + g * 64, p.relu2, false);
+      drain32(taddr + 32, row2_u32, 4u, p.scale2 + g * 64 + 32, p.shift2 + g * 64 + 32, p.relu2, false);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&chain_empty[cc & 1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(map_out2, slice2_u32, g * 64, tile_row(cc));
+        tma_store_commit();
+      }
+    };
+    if (lane == 0 && par < total_main) issue_res(par);
+#pragma unroll 1
+    for (int q = par; q < total_main; q += 2) {
+      const int c = q >> 2, n = q & 3, b = q & (NB - 1);
+      if (lane == 0 && q + 2 < total_main) {
+        if (q >= 2) {                                        // the group's other staging tile: store read, chained MMAs on it retired
+          tma_store_wait_read();
+          mbar_wait(&buf_free[b ^ 2], (uint32_t)((q - 2) >> 2) & 1u);
+        }
+        issue_res(q + 2);
+      }
+      if (par == 1 && n == 1 && c >= 1) chain_epilogue(c - 1);   // its MMAs were issued behind sub-tile (c - 1, 3)
+      mbar_wait(&tmem_full[par], (uint32_t)((q >> 1) & 1));
+      tc_fence_after();
+      mbar_wait(&res_bar[ew * 2 + (b >> 1)], (uint32_t)(q >> 2) & 1u);
+      const uint32_t my_row_u32 = row0_u32 + (uint32_t)b * BUF_BYTES;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + par * BN + g * 64;
+      const int n0 = n * BN + g * 64;
+      drain32(taddr, my_row_u32, 0u, p.scale1 + n0, p.shift1 + n0, p.relu1, true);
+      drain32(taddr + 32, my_row_u32, 4u, p.scale1 + n0 + 32, p.shift1 + n0 + 32, p.relu1, true);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[par]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&staged[b]);
+        tma_store_2d(map_out1, slice0_u32 + (uint32_t)b * BUF_BYTES, n0, tile_row(c));
+        tma_store_commit();
+      }
+    }
+    if (par == 1 && J > 0) chain_epilogue(J - 1);
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // conv1_7x7_s2 as a "line" kernel.  After space-to-depth the layer is a 4x4 / stride-1 convolution
 // over 16-channel pixels.  One tile = one output line (112 pixels): the 4-row input patch is loaded once
 // and each of the 16 taps is a K=16 UMMA on a row-shifted view of it; the whole 64 x 256 weight matrix
@@ -2391,6 +2661,8 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
   { const char* e = getenv("MIMAMO_CHAIN_DEBUG"); p.debug = e ? atoi(e) : 0; }
   const char* rwe = getenv("MIMAMO_CHAIN_SMEM");
   const bool rw = p.nkb1 == 1 && L1.Cout == ChainSmemCfg::N1 && L2.Cout == ChainSmemCfg::N2 && !(rwe && rwe[0] == '0');
+  // ... and with streamed weights for the stage-3 shape
+  const bool st = L1.Cin_p == ChainStreamCfg::K1 && L1.Cout == ChainStreamCfg::N1 && L2.Cout == ChainStreamCfg::N2 && !(rwe && rwe[0] == '0');
   const uint32_t es[2] = {1, 1};
   const uint32_t abox[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
   {
@@ -2408,7 +2680,7 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
   int rc = weight_map(L1, &p.b1, BN);
   if (!rc) rc = weight_map(L2, &p.b2, L2.Cout);
   // store / residual boxes: 32 rows x 32 columns per warp (L2 hand-over) or x 64 columns per warp pair (on-chip hand-over)
-  const int box_bn = rw ? 256 : BN;
+  const int box_bn = (rw || st) ? 256 : BN;
   if (!rc) rc = out_map_flat(&p.out1, L1.elem, out1, L1.Cout, L1.Cout, M, box_bn, 32);
   if (!rc) rc = out_map_flat(&p.res, L1.elem, const_cast<void*>(residual), ld_res, L1.Cout, M, box_bn, 32);
   if (!rc) rc = out_map_flat(&p.out2, L2.elem, out2, ldc2, L2.Cout, M, box_bn, 32);
@@ -2420,6 +2692,8 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
     MM_CUDA(cudaFuncSetAttribute(conv_chain_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg<BN>::kSmemBytes));
     MM_CUDA(cudaFuncSetAttribute(conv_chain_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmemCfg::kSmemBytes));
     MM_CUDA(cudaFuncSetAttribute(conv_chain_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainSmemCfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainStreamCfg::kSmemBytes));
+    MM_CUDA(cudaFuncSetAttribute(conv_chain_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainStreamCfg::kSmemBytes));
     attr_set.mark();
   }
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
@@ -2439,6 +2713,9 @@ int chain_forward(const ConvLayer& L1, const ConvLayer& L2, const void* a, int M
   if (rw) {
     if (bf) conv_chain_smem_kernel<true><<<grid, kGemmThreads, ChainSmemCfg::kSmemBytes, stream>>>(p);
     else conv_chain_smem_kernel<false><<<grid, kGemmThreads, ChainSmemCfg::kSmemBytes, stream>>>(p);
+  } else if (st) {
+    if (bf) conv_chain_stream_kernel<true><<<grid, kGemmThreads, ChainStreamCfg::kSmemBytes, stream>>>(p);
+    else conv_chain_stream_kernel<false><<<grid, kGemmThreads, ChainStreamCfg::kSmemBytes, stream>>>(p);
   } else {
     if (bf) conv_chain_kernel<BN, true><<<grid, kGemmThreads, ChainCfg<BN>::kSmemBytes, stream>>>(p);
     else conv_chain_kernel<BN, false><<<grid, kGemmThreads, ChainCfg<BN>::kSmemBytes, stream>>>(p);

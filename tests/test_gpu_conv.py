@@ -82,7 +82,7 @@ CHAIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("rw", ["1", "0"])          # on-chip hand-over with resident weights (K1 = 64, N2 = 64 shapes) / hand-over through L2
+@pytest.mark.parametrize("rw", ["1", "0"])          # on-chip hand-over (stage-2 shape: resident weights, stage-3 shape: streamed) / hand-over through L2
 @pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(str(v) for v in c))
 def test_conv_chain(cuda, case, rw, monkeypatch):
     """conv_chain_kernel (increase + residual + ReLU, then the next block's reduce + ReLU in one launch) against the two
@@ -90,8 +90,8 @@ def test_conv_chain(cuda, case, rw, monkeypatch):
     output of the first, exactly like the layer-by-layer path)."""
     import _native
     M, K1, N1, N2 = case
-    if rw == "0" and K1 != 64:
-        pytest.skip("only K1 = 64 shapes have an on-chip variant to switch off")
+    if rw == "0" and (K1, N1, N2) not in ((64, 256, 64), (128, 512, 128)):
+        pytest.skip("only the ResNet50 stage-2 / stage-3 shapes have an on-chip variant to switch off")
     monkeypatch.setenv("MIMAMO_CHAIN_SMEM", rw)
     gen = torch.Generator().manual_seed(sum(case))
     x = torch.randn(M, K1, generator=gen).to(torch.bfloat16)
