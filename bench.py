@@ -610,6 +610,9 @@ def main():
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up, device-timed leg only")
     args = ap.parse_args()
     if args.impl == "reference":
+        # the reference's CPU path on the host cores: its own get_device() picks cuda:0 whenever a GPU is visible (and then asserts
+        # on the CPU tensors it is fed), so the arm hides the GPUs from this process before CUDA is initialised
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
         return run_reference(args)
     ctx = Ctx(args)
     {"e2e": bench_e2e, "pyramid224": bench_pyramid224, "resnet512": bench_resnet512, "videos": bench_videos}[args.config](ctx)
