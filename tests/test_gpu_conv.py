@@ -77,6 +77,8 @@ CHAIN_CASES = [
     (2 * 56 * 56, 64, 256, 64),        # ResNet50 stage 2: one K block, two 128-wide sub-tiles per M tile, 64-wide chained layer
     (3 * 28 * 28 + 5, 128, 512, 128),  # stage 3, M not a multiple of 128 (TMA clips the last tile)
     (100, 64, 128, 64),                # a single partial M tile
+    (100, 64, 256, 64),                # ... through the on-chip hand-over kernels (one CTA, one tile, TMA clips rows >= M)
+    (60, 128, 512, 128),
     (300 * 128, 64, 256, 64),          # more M tiles than SMs: the software-pipelined sequence over several tiles per CTA
     (149 * 128, 128, 512, 128),        # 149 tiles: one CTA owns two M tiles, the others one
 ]
