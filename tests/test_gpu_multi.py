@@ -1,6 +1,6 @@
 """Multi-GPU determinism (SURVEY.md sections 4(v), 8(e)): the gathered per-video predictions of multi_gpu.run_videos at
-world size 2 (NCCL, one process per GPU) are BIT-IDENTICAL to a single process running every video -- videos are never
-split across ranks and no kernel depends on what else shares its batch.  Needs two GPUs (skipped otherwise)."""
+world size 2 / 4 / 8 (NCCL, one process per GPU) are BIT-IDENTICAL to a single process running every video -- videos are
+never split across ranks and no kernel depends on what else shares its batch.  Each case needs that many GPUs (skipped otherwise)."""
 import os
 import sys
 
@@ -48,9 +48,10 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_ranks_bit_identical_to_one(cuda):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_bit_identical_to_one(cuda, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     tester = _tester()
     single = [tester.predict_frames(v.to(cuda)).cpu().numpy() for v in _videos()]      # one video at a time, like Tester.test
     from multi_gpu import run_videos
@@ -60,7 +61,7 @@ def test_two_ranks_bit_identical_to_one(cuda):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]
