@@ -436,7 +436,9 @@ def bench_pyramid224(ctx):
     args, dev = ctx.args, ctx.dev
     from phase_difference_extractor import Phase_Difference_Extractor
     W, H, nb = PYR["windows"], PYR["H"], PYR["nbands"]
-    pde = Phase_Difference_Extractor(height=PYR["height"], nbands=nb, extract_level=PYR["levels"])
+    height = args.pyr_height or PYR["height"]
+    levels = [int(v) for v in args.pyr_levels.split(",")] if args.pyr_levels else list(PYR["levels"])
+    pde = Phase_Difference_Extractor(height=height, nbands=nb, extract_level=levels)
     g = torch.Generator().manual_seed(200 + ctx.rank)
     frames_h = torch.rand(W, T, H, H, generator=g).pin_memory()                # distinct frames: nothing to de-duplicate
     frames = frames_h.to(dev)
@@ -468,7 +470,7 @@ def bench_pyramid224(ctx):
     ms_clip = ctx.timed(step_clip, steps)
     step_e2e()
     ms_e2e = ctx.timed(step_e2e, steps)
-    bytes_per_window = 4 * T * H * H + 4 * nb * (T - 1) * sum((H >> l) ** 2 for l in range(3))
+    bytes_per_window = 4 * T * H * H + 4 * nb * (T - 1) * sum((H >> (l - 1)) ** 2 for l in levels)
     _, peak, src = peaks()
     world = ctx.world
     gbs = bytes_per_window * W * steps / (ms / 1e3) / 1e9
@@ -477,7 +479,7 @@ def bench_pyramid224(ctx):
         "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[2]: steerable pyramid + phase difference only, %d windows x %d DISTINCT frames of %dx%d per GPU, "
-                               "height 5, 8 orientations, levels [1,2,3]" % (W, T, H, H),
+                               "height %d, 8 orientations, levels %s" % (W, T, H, H, height, str(levels).replace(" ", "")),
                    "l2": "inputs + outputs (%.1f GB per step) exceed the 126 MB L2" % (bytes_per_window * W / 1e9)},
         "e2e": {"value": world * W * steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": world * frames_h.numel() * 4,
@@ -606,6 +608,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="e2e", choices=["e2e", "pyramid224", "resnet512", "videos"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pyr-height", type=int, default=None,
+                    help="pyramid224 only: pyramid height (SURVEY 8(d) secondary number: 6 = four oriented scales, the maximum at 224x224)")
+    ap.add_argument("--pyr-levels", default=None, help="pyramid224 only: comma-separated extract levels, e.g. 1,2,3,4")
     ap.add_argument("--layers", action="store_true", help="print per-launch GEMM times to stderr")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up, device-timed leg only")
     args = ap.parse_args()

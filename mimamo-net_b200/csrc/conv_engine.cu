@@ -59,13 +59,16 @@ struct ConvParams {
   void* out;
   int ldc, ld_res;
   int relu;
-  int debug;                 // timing experiments only (MIMAMO_DEBUG): 1 = epilogue skips math+store, 2 = line kernel issues 4 of 16 UMMAs
+  int debug;                 // timing experiments only (MIMAMO_DEBUG): 1 = epilogue skips math+store (layers without residual), 2 = line kernel issues 4 of 16 UMMAs, 4 / 8 = halo kernel (see there)
   int pair;                  // conv_gemm_kernel launched as 2-CTA clusters: the two CTAs work on adjacent M tiles of the same N tile and
                              // each fetches half of every weight box, multicast into both shared memories (halves the L2->SM weight traffic)
   int store_mode;            // epilogue TMA store granularity: 0 = per warp (32 rows, flat layers), 1 = per column group, 2 = whole tile
   int resident_w;            // halo kernel: the whole 3x3 weight set stays in shared memory (Cin_p == 64, 9 taps <= kBStages boxes)
   int res_tma;               // residual fetched by TMA straight into the output staging tile (flat 256-wide layers, per-warp stores)
   alignas(64) CUtensorMap res_map;   // ... through this map: the residual tensor with the geometry of the output map
+  int sub, sub_pad;          // strided k x k layers: tap (kh, kw) reads a DENSE box of one (row parity, column parity) sub-lattice of
+                             // the input through sub_map[2 * row parity + column parity] (conv_forward); sub_pad = the layer's padding
+  alignas(64) CUtensorMap sub_map[4];
 };
 
 // ---------------------------------------------------------------------------------------
@@ -473,7 +476,7 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, const CUtens
         sync_store_group();
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + half * COLS;
-      if ((p.debug & 1) && !tmem_empty_leader) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
+      if ((p.debug & 1) && !HAS_RES && !tmem_empty_leader) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tmem_empty[acc]); continue; }
 #pragma unroll 1
       for (int c0 = 0; c0 < COLS; c0 += 32, ++qc) {
         uint32_t v[32];
@@ -590,6 +593,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (p.sub) for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.sub_map[i]);
     if (RES == 2 || (HAS_RES && p.res_tma)) {
       tma_prefetch_desc(&p.res_map);
       for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
@@ -628,6 +632,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int step_w = p.bw * p.stride, step_h = p.bh * p.stride, pad = p.pad, bn = p.bn;
     const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    const uint64_t mapS = reinterpret_cast<uint64_t>(&p.sub_map[0]);
+    const bool sub = p.sub != 0;                               // stride-2 k x k: per-tap sub-lattice maps (see conv_forward)
+    const int sub_pad = p.sub_pad;
     int stage = 0; uint32_t parity = 1;                        // producer waits on empty with parity phase ^ 1
     uint32_t dA = sA0, dB = sB0, fb = full0, eb = empty0;
 #pragma unroll 1
@@ -656,6 +663,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (leader) {
               bar_expect_tx_u32(fb, tx_bytes);
               if (mode == 0) tma2d_u32(dA, mapA, fb, cb * kBlockK, c1);
+              else if (sub) tma4d_u32(dA, mapS + (uint64_t)((((kh - sub_pad) & 1) << 1) | ((kw - sub_pad) & 1)) * sizeof(CUtensorMap), fb,
+                                      cb * kBlockK, c1 + ((kw - sub_pad) >> 1), c2 + ((kh - sub_pad) >> 1), c3);
               else tma4d_u32(dA, mapA, fb, cb * kBlockK, c1 + kw, c2 + kh, c3);
               if (pair) tma2d_multicast_u32(dB + rank * (Cfg::kBStageBytes / 2), mapB, fb, kcol, n0 + (int)rank * (BLOCK_N / 2), (uint16_t)3);
               else tma2d_u32(dB, mapB, fb, kcol, n0);
@@ -763,6 +772,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    if (p.sub) for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.sub_map[i]);
     if (RES == 2 || (HAS_RES && p.res_tma)) {
       tma_prefetch_desc(&p.res_map);
       for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
@@ -792,6 +802,9 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB), full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const uint32_t lfull0 = mapa_u32(full0, 0);              // the leader's full barriers (own ones when rank == 0)
     const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    const uint64_t mapS = reinterpret_cast<uint64_t>(&p.sub_map[0]);
+    const bool sub = p.sub != 0;
+    const int sub_pad = p.sub_pad;
     int stage = 0; uint32_t parity = 1;
     uint32_t dA = sA0, dB = sB0, fb = full0, lfb = lfull0, eb = empty0;
 #pragma unroll 1
@@ -820,6 +833,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (leader) {
               if (rank == 0) bar_expect_tx_u32(fb, pair_tx);   // bytes of BOTH CTAs' boxes
               if (mode == 0) tma2d_2sm_u32(dA, mapA, lfb, cb * kBlockK, c1);
+              else if (sub) tma4d_2sm_u32(dA, mapS + (uint64_t)((((kh - sub_pad) & 1) << 1) | ((kw - sub_pad) & 1)) * sizeof(CUtensorMap), lfb,
+                                          cb * kBlockK, c1 + ((kw - sub_pad) >> 1), c2 + ((kh - sub_pad) >> 1), c3);
               else tma4d_2sm_u32(dA, mapA, lfb, cb * kBlockK, c1 + kw, c2 + kh, c3);
               tma2d_2sm_u32(dB, mapB, lfb, kcol, n0);
             }
@@ -995,7 +1010,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
     const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a), fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
     const uint32_t tfull0 = smem_u32(tmem_full), tempty0 = smem_u32(tmem_empty);
-    const uint32_t row16 = (uint32_t)line * 8u;              // one padded line in (address >> 4) units
+    // timing experiments (MIMAMO_DEBUG): 4 = every tap reads the un-shifted patch (is the shifted start address slower?),
+    // 8 = one tap per kernel row (12 of 36 UMMAs per channel block: does the tile time follow the UMMA count?)
+    const bool dbg_noshift = (p.debug & 4) != 0, dbg_third = (p.debug & 8) != 0;
+    const uint32_t row16 = dbg_noshift ? 0u : (uint32_t)line * 8u;   // one padded line in (address >> 4) units
+    const uint32_t px16 = dbg_noshift ? 0u : 8u;                     // one pixel (128 B)
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     int local = 0;
 #pragma unroll 1
@@ -1016,8 +1035,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (leader) {
             const uint32_t b_lo = b_lo0 + sb * (Cfg::kBStageBytes >> 4);
             umma_kblock(d_tmem, a_row, b_lo, idesc, (cb | kh) != 0 ? 1u : 0u);
-            umma_kblock(d_tmem, a_row + 8, b_lo + (BLOCK_N * 128 >> 4), idesc, 1u);
-            umma_kblock(d_tmem, a_row + 16, b_lo + 2 * (BLOCK_N * 128 >> 4), idesc, 1u);
+            if (!dbg_third) {
+              umma_kblock(d_tmem, a_row + px16, b_lo + (BLOCK_N * 128 >> 4), idesc, 1u);
+              umma_kblock(d_tmem, a_row + 2 * px16, b_lo + 2 * (BLOCK_N * 128 >> 4), idesc, 1u);
+            }
             if (!resident) commit_u32(eb0 + sb * 8);
             if (kh == 2) {
               commit_u32(ea0 + sa * 8);
@@ -2803,6 +2824,16 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
       if (H == Ho * L.stride && residual == nullptr) { Hv = Ho * B; Ho = Hv; B = 1; }
     }
   }
+  // Stride-2 k x k layers (PhaseNet's second convolution of every block, api/mimamo_net.py:72): input pixel 2y + kh - pad lies
+  // on the sub-lattice of row parity (kh - pad) & 1 at index y + ((kh - pad) >> 1), so every tap is a DENSE box over one of
+  // four strided views (row parity x column parity) instead of an element-strided box that walks the skipped pixels (those
+  // layers ran at 23-55 % of their tensor floor).  Indices outside a view are the convolution's zero padding.
+  bool sub = false;
+  {
+    const char* e = getenv("MIMAMO_STRIDED_VIEW");
+    sub = L.ksize > 1 && L.stride == 2 && W >= 2 && H >= 2 && !(e && e[0] == '0');
+    if (sub) vstride = 1;
+  }
   // choose the output box (bw x bh x bn <= 128 pixels) that wastes the fewest MMA rows
   int best_bw = 1, best_bh = 1, best_bn = 1;
   long long best_tiles = -1;
@@ -2823,7 +2854,7 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   const uint64_t strides[3] = {pix_pitch * 2, (uint64_t)W * in_pitch * 2 * (uint64_t)(L.stride / vstride), (uint64_t)H * W * in_pitch * 2};
   const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(best_bw * vstride), (uint32_t)(best_bh * vstride), (uint32_t)best_bn};
   const uint32_t es[4] = {1, (uint32_t)vstride, (uint32_t)vstride, 1};
-  int rc = encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
+  int rc = sub ? 0 : encode_map(&ma, L.elem, 4, x, dims, strides, box, es);
   if (rc) return rc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -2836,6 +2867,20 @@ int conv_forward(const ConvLayer& L, const void* x, int B, int H, int W, void* o
   p.a_rows = best_bw * best_bh * best_bn;
   p.m_tiles = (int)best_tiles;
   p.stride = vstride;                           // the producer steps boxes in units of the tensor the map describes
+  if (sub) {
+    p.sub = 1; p.sub_pad = L.pad; p.pad = 0;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const uint64_t sdims[4] = {(uint64_t)in_channels, (uint64_t)((W - pw + 1) / 2), (uint64_t)((H - ph + 1) / 2), (uint64_t)B};
+        const uint64_t sstr[3] = {(uint64_t)in_pitch * 4, (uint64_t)W * in_pitch * 4, (uint64_t)H * W * in_pitch * 2};
+        const uint32_t sbox[4] = {(uint32_t)kBlockK, (uint32_t)best_bw, (uint32_t)best_bh, (uint32_t)best_bn};
+        const uint32_t ses[4] = {1, 1, 1, 1};
+        const uint16_t* base = reinterpret_cast<const uint16_t*>(x) + ((size_t)ph * W + pw) * in_pitch;
+        rc = encode_map(&p.sub_map[ph * 2 + pw], L.elem, 4, base, sdims, sstr, sbox, ses);
+        if (rc) return rc;
+      }
+    ma = p.sub_map[0];
+  }
   p.pair = pair_wanted(bn_eff, p.num_k_blocks, p.m_tiles, false);
   if (p.pair == 2) p.idesc = make_idesc2(bn_eff, L.elem);
   rc = weight_map(L, &mb, p.pair ? bn_eff / 2 : bn_eff);

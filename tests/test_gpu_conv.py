@@ -23,8 +23,11 @@ CASES = [
     (3, 7, 9, 256, 512, 1, 2, 0, 0, False),      # odd extents: the view ends on the last sampled pixel
     (5, 14, 14, 512, 256, 1, 2, 0, 1, False),    # even extents: sampled rows merge across images (126-row tiles)
     (40, 28, 28, 256, 512, 1, 2, 0, 0, False),   # ... with more tiles than one wave of CTA pairs
-    (2, 48, 48, 64, 64, 3, 2, 1, 1, False),      # PhaseNet stride-2 3x3
+    (2, 48, 48, 64, 64, 3, 2, 1, 1, False),      # PhaseNet stride-2 3x3: every tap a dense box over one of four sub-lattice views
     (3, 12, 12, 256, 256, 3, 2, 1, 1, False),
+    (40, 24, 24, 128, 128, 3, 2, 1, 1, False),   # ... more tiles than CTAs
+    (3, 9, 7, 64, 128, 3, 2, 1, 0, False),       # odd extents: the odd sub-lattices are one row / column shorter
+    (2, 14, 14, 64, 64, 5, 2, 2, 1, False),      # 5x5: tap offsets -2 .. 2
     (2, 14, 14, 256, 1024, 1, 1, 0, 1, True),    # residual add + ReLU epilogue
     (1, 7, 7, 512, 2048, 1, 1, 0, 1, True),
     (300, 7, 7, 64, 64, 3, 1, 1, 0, False),      # more tiles than SMs: persistent loop + TMEM double buffer
@@ -33,13 +36,23 @@ CASES = [
 
 # MIMAMO_PAIR "<mode><force>": "0" single CTAs; "11" forces 2-CTA clusters with multicast weight boxes on every 256-wide
 # layer; "21" forces the cta_group::2 UMMA kernel (shapes this small would not select them on their own)
-@pytest.mark.parametrize("pair", ["0", "11", "21"])
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c))
-def test_conv_engine(cuda, case, pair, monkeypatch):
+def _cases_with_modes():
+    out = []
+    for c in CASES:
+        for pair in ("0", "11", "21"):
+            if pair != "0" and c[4] % 256 != 0:
+                continue                                  # pair modes only exist for 256-wide tiles
+            out.append(pytest.param(c, pair, "1", id="x".join(str(v) for v in c) + "-pair" + pair))
+        if c[6] == 2:                                     # strided layers: also the element-strided boxes (MIMAMO_STRIDED_VIEW=0)
+            out.append(pytest.param(c, "0", "0", id="x".join(str(v) for v in c) + "-elemstride"))
+    return out
+
+
+@pytest.mark.parametrize("case,pair,view", _cases_with_modes())
+def test_conv_engine(cuda, case, pair, view, monkeypatch):
     import _native
-    if pair != "0" and case[4] % 256 != 0:
-        pytest.skip("pair mode only exists for 256-wide tiles")
     monkeypatch.setenv("MIMAMO_PAIR", pair)
+    monkeypatch.setenv("MIMAMO_STRIDED_VIEW", view)
     B, H, W, Cin, Cout, k, s, p, relu, use_res = case
     gen = torch.Generator().manual_seed(sum(case[:8]))
     x = torch.randn(B, H, W, Cin, generator=gen).to(torch.bfloat16)
@@ -84,16 +97,24 @@ CHAIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("rw", ["1", "0"])          # on-chip hand-over (stage-2 shape: resident weights, stage-3 shape: streamed) / hand-over through L2
-@pytest.mark.parametrize("case", CHAIN_CASES, ids=lambda c: "x".join(str(v) for v in c))
+def _chain_cases():
+    # rw = "1": on-chip hand-over where a variant exists (stage-2 shape: resident weights, stage-3 shape: streamed), "0": hand-over
+    # through L2 -- only distinct for the two ResNet50 shapes that have an on-chip variant to switch off
+    out = []
+    for c in CHAIN_CASES:
+        out.append(pytest.param(c, "1", id="x".join(str(v) for v in c) + "-1"))
+        if c[1:] in ((64, 256, 64), (128, 512, 128)):
+            out.append(pytest.param(c, "0", id="x".join(str(v) for v in c) + "-0"))
+    return out
+
+
+@pytest.mark.parametrize("case,rw", _chain_cases())
 def test_conv_chain(cuda, case, rw, monkeypatch):
     """conv_chain_kernel (increase + residual + ReLU, then the next block's reduce + ReLU in one launch) against the two
     layers computed separately in fp32 on the same bf16-rounded operands (the chained layer reads the bf16-rounded
     output of the first, exactly like the layer-by-layer path)."""
     import _native
     M, K1, N1, N2 = case
-    if rw == "0" and (K1, N1, N2) not in ((64, 256, 64), (128, 512, 128)):
-        pytest.skip("only the ResNet50 stage-2 / stage-3 shapes have an on-chip variant to switch off")
     monkeypatch.setenv("MIMAMO_CHAIN_SMEM", rw)
     gen = torch.Generator().manual_seed(sum(case))
     x = torch.randn(M, K1, generator=gen).to(torch.bfloat16)
