@@ -361,7 +361,7 @@ def bench_e2e(ctx):
         ctx.sampler.start()
     ms, launches, gemm_ms, gemm_n, issued = ctx.gemm_profile(step_device, args.steps)
 
-    def stage_ms(fn, reps=3):
+    def stage_ms(fn, reps=10):
         fn()
         return ctx.timed(fn, reps) / reps
 

@@ -290,12 +290,20 @@ struct MapGeom {
 
 constexpr int kMapThreads = 320;      // upper bound of the whole-map kernel's block size (two CTAs per SM keep ~100 registers each)
 
-template <bool NHWC16>
-__global__ void __launch_bounds__(kMapThreads, 2)
+//
+// SZ / NTHR > 0 fix the map size (SZ x SZ) and the block size at compile time (the Tester configuration: 48x48 maps at 288
+// threads, 24x24 at 160).  With run-time extents two thirds of the instructions the kernel issues are integer address
+// arithmetic (SASS: 1230 IMAD / IADD3 / ISETP / LEA against 640 FFMA / FADD / FMUL); with constant extents the tile strides,
+// the (i / d, i % d) walks and the loop trip counts fold into immediates.  Same operations on the same values in the same
+// order: bit-identical to the generic instantiation (SZ = NTHR = 0; MIMAMO_TAIL_GENERIC=1 forces it, cross-check test).
+template <bool NHWC16, int SZ, int NTHR>
+__global__ void __launch_bounds__(NTHR > 0 ? NTHR : kMapThreads, 2)
 phase_tail_map_kernel(const float* __restrict__ coeff, void* __restrict__ out_, const MapGeom g, const int* __restrict__ root,
                       int nb, int coeff_T, int polar, int mode, int pitch, int c_off) {
   extern __shared__ __align__(16) unsigned char raw[];
-  const int rin = g.rin, cin = g.cin, tcp = g.tcp, trp = g.trp, rows = g.rows, cols = g.cols;
+  const int rows = SZ > 0 ? SZ : g.rows, cols = SZ > 0 ? SZ : g.cols;
+  const int trp = SZ > 0 ? (SZ + 3) / 4 * 4 : g.trp, tcp = SZ > 0 ? (SZ + 3) / 4 * 4 : g.tcp;
+  const int rin = trp + 2 * kHalo, cin = tcp + 12;               // as make_map_geom
   const int n_in = rin * cin, n_out = trp * tcp, n_map = rows * cols;
   const int n_map_p = (n_map + 3) & ~3;                          // keeps every array below 16-byte aligned
   double* cum = reinterpret_cast<double*>(raw);                  // [n_map] running unwrap correction
@@ -313,7 +321,7 @@ phase_tail_map_kernel(const float* __restrict__ coeff, void* __restrict__ out_, 
   const int band = (int)(map - win * nb);
   const int T = g.T;
   const int n_slots = mode == 0 ? T - 1 : (mode == 1 ? T : 2 * (T - 1));
-  const int nthr = blockDim.x;
+  const int nthr = NTHR > 0 ? NTHR : (int)blockDim.x;
   const int groups = tcp >> 2;
 
   for (int i = threadIdx.x; i < n_map; i += nthr) { cum[i] = 0.0; prev[i] = 0.f; }
@@ -434,7 +442,7 @@ phase_tail_map_kernel(const float* __restrict__ coeff, void* __restrict__ out_, 
     }
   };
   const float lim = 15.7079632679489656f;                          // 5*pi
-  constexpr int kMaxOwned = NHWC16 ? 12 : 1;                      // pixels per thread: 56 * 56 / 288 rounded up
+  constexpr int kMaxOwned = !NHWC16 ? 1 : (SZ > 0 ? (SZ * SZ + NTHR - 1) / NTHR : 12);   // pixels per thread (generic: 56 * 56 / 288 rounded up)
   uint32_t lo[kMaxOwned], hi[kMaxOwned];                          // NHWC16: four fp16 channels per owned pixel being collected
   // (W) results of frame t: mean removal, clamp, store
   auto stage_w = [&](int t) {
@@ -577,6 +585,15 @@ static int map_threads(const MapGeom& g) {
   }
 }
 
+// Which compile-time specialisation of the whole-map kernel fits (0 = generic): the Tester configuration's two map sizes.
+static int map_special(const MapGeom& g, int threads) {
+  const char* e = getenv("MIMAMO_TAIL_GENERIC");
+  if (e && e[0] == '1') return 0;
+  if (g.rows == 48 && g.cols == 48 && threads == 288) return 48;
+  if (g.rows == 24 && g.cols == 24 && threads == 160) return 24;
+  return 0;
+}
+
 static DeviceOnce g_tail_ready;               // the __constant__ taps and the function attribute are per device
 static int tail_setup() {
   if (!g_tail_ready.need()) return MIMAMO_OK;
@@ -584,8 +601,12 @@ static int tail_setup() {
   for (int d = 0; d < kTaps; ++d) taps[d] = (float)exp(-(double)((d - kHalo) * (d - kHalo)) / 8.0);   // std = 2
   MM_CUDA(cudaMemcpyToSymbol(c_gauss, taps, sizeof(taps)));
   MM_CUDA(cudaFuncSetAttribute(phase_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<false, 48, 288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<true, 48, 288>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<false, 24, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+  MM_CUDA(cudaFuncSetAttribute(phase_tail_map_kernel<true, 24, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
   g_tail_ready.mark();
   return MIMAMO_OK;
 }
@@ -612,8 +633,13 @@ int phase_extract_launch(const float* coeff, int64_t n_maps, int T, int rows, in
   const char* force = getenv("MIMAMO_TAIL");       // "tiled": run whole maps through the tiled kernel too (cross-check)
   if (ntiles == 1 && !(force && force[0] == 't')) {
     const MapGeom mgeo = make_map_geom(T, rows, cols);
-    phase_tail_map_kernel<false><<<(unsigned)n_maps, map_threads(mgeo), map_smem(mgeo), stream>>>(coeff, out, mgeo, root, nb, coeff_T > 0 ? coeff_T : T,
-                                                                                        polar, mode, 0, 0);
+    const int thr = map_threads(mgeo), cT = coeff_T > 0 ? coeff_T : T;
+    const size_t smem = map_smem(mgeo);
+    switch (map_special(mgeo, thr)) {
+      case 48: phase_tail_map_kernel<false, 48, 288><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out, mgeo, root, nb, cT, polar, mode, 0, 0); break;
+      case 24: phase_tail_map_kernel<false, 24, 160><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out, mgeo, root, nb, cT, polar, mode, 0, 0); break;
+      default: phase_tail_map_kernel<false, 0, 0><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out, mgeo, root, nb, cT, polar, mode, 0, 0);
+    }
     MM_LAUNCH_OK();
     return MIMAMO_OK;
   }
@@ -644,8 +670,13 @@ int phase_extract_nhwc16_launch(const float* coeff, int64_t n_maps, int T, int r
   int rc = tail_setup();
   if (rc) return rc;
   const MapGeom mgeo = make_map_geom(T, rows, cols);
-  phase_tail_map_kernel<true><<<(unsigned)n_maps, map_threads(mgeo), map_smem(mgeo), stream>>>(coeff, out16, mgeo, root, nb,
-                                                                                                 coeff_T > 0 ? coeff_T : T, polar, 0, pitch, c_off);
+  const int thr = map_threads(mgeo), cT = coeff_T > 0 ? coeff_T : T;
+  const size_t smem = map_smem(mgeo);
+  switch (map_special(mgeo, thr)) {
+    case 48: phase_tail_map_kernel<true, 48, 288><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out16, mgeo, root, nb, cT, polar, 0, pitch, c_off); break;
+    case 24: phase_tail_map_kernel<true, 24, 160><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out16, mgeo, root, nb, cT, polar, 0, pitch, c_off); break;
+    default: phase_tail_map_kernel<true, 0, 0><<<(unsigned)n_maps, thr, smem, stream>>>(coeff, out16, mgeo, root, nb, cT, polar, 0, pitch, c_off);
+  }
   MM_LAUNCH_OK();
   return MIMAMO_OK;
 }

@@ -280,3 +280,33 @@ def test_map_kernel_matches_tiled_kernel(cuda, monkeypatch):
             b = spp.extract_phase(coeff, **kw)
             assert torch.equal(a, b), (shape, kw)
             assert (a.cpu() - O.extract_phase(coeff.cpu(), **kw)).abs().max().item() < PHASE_TOL
+
+
+def test_size_specialised_tail_is_bit_identical(cuda, monkeypatch):
+    """The whole-map tail kernel is instantiated with compile-time extents for the Tester configuration's 48x48 and 24x24 maps
+    (constant strides / trip counts instead of run-time index arithmetic).  MIMAMO_TAIL_GENERIC=1 forces the run-time-extent
+    instantiation: same operations in the same order, so the same bits -- fp32 outputs in every mode and the fp16 NHWC feed."""
+    from phase_difference_extractor import Phase_Difference_Extractor, Steerable_Pyramid_Phase
+    from sampler.snippet_sampler import window_index
+    spp = Steerable_Pyramid_Phase(height=4, nbands=2, scale_factor=2, device=cuda, extract_level=1)
+    gen = torch.Generator().manual_seed(21)
+    for shape in ((5, 2, 13, 48, 48, 2), (5, 2, 13, 24, 24, 2), (3, 2, 2, 48, 48, 2)):
+        coeff = torch.randn(*shape, generator=gen).to(cuda)
+        for kw in ({}, {"return_phase": True}, {"return_both": True}):
+            monkeypatch.delenv("MIMAMO_TAIL_GENERIC", raising=False)
+            a = spp.extract_phase(coeff, **kw)
+            monkeypatch.setenv("MIMAMO_TAIL_GENERIC", "1")
+            b = spp.extract_phase(coeff, **kw)
+            assert torch.equal(a, b), (shape, kw)
+            assert (a.cpu() - O.extract_phase(coeff.cpu(), **kw)).abs().max().item() < PHASE_TOL
+    pde = Phase_Difference_Extractor(height=4, nbands=2, extract_level=[1, 2])
+    frames = torch.rand(40, 48, 48, generator=gen).to(cuda)
+    idx = window_index(0, 40, 40, 12).to(cuda, torch.int32)
+    monkeypatch.delenv("MIMAMO_TAIL_GENERIC", raising=False)
+    fast = pde.phasenet_operands(frames, idx)
+    fast32 = pde.phase_difference_indexed(frames, idx)
+    monkeypatch.setenv("MIMAMO_TAIL_GENERIC", "1")
+    slow = pde.phasenet_operands(frames, idx)
+    slow32 = pde.phase_difference_indexed(frames, idx)
+    for x, y in zip(list(fast) + list(fast32), list(slow) + list(slow32)):
+        assert x.shape == y.shape and torch.equal(x, y)
