@@ -1,12 +1,10 @@
 #!/bin/bash
-# scratch GPU round trip: size-specialised tail kernel: parity + A/B timing
+# 2-GPU sanity of the final build: NCCL determinism test + the two multi-GPU bench lines
 mkdir -p gpurun_out
-for f in test_gpu_pyramid test_gpu_preproc; do
-  timeout 600 python -m pytest tests/$f.py -q -m gpu -x > gpurun_out/t_$f.log 2>&1; echo "$f exit $?"; tail -3 gpurun_out/t_$f.log
-done
-for v in 0 1 0 1; do
-  MIMAMO_TAIL_GENERIC=$v timeout 300 python bench.py --config e2e --quick --steps 8 --warmup 3 > gpurun_out/exp_e2e_generic$v.json 2> gpurun_out/exp_e2e_generic$v.err; echo "e2e generic=$v exit $?"
+timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu -x > gpurun_out/test_gpu_multi_2gpu.log 2>&1; echo "multi test exit $?"; tail -2 gpurun_out/test_gpu_multi_2gpu.log
+for c in e2e videos; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config $c --steps 5 --warmup 3 > gpurun_out/bench_${c}_2gpu.json 2> gpurun_out/bench_${c}_2gpu.err; echo "bench $c 2gpu exit $?"
   python -c "
-import json; d=json.loads([l for l in open('gpurun_out/exp_e2e_generic$v.json') if l.startswith('{')][-1]); print('generic=$v', d['ms_per_step'], d['value'], d.get('stage_ms'))"
+import json; d=json.loads([l for l in open('gpurun_out/bench_${c}_2gpu.json') if l.startswith('{')][-1]); print('$c', d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'])"
 done
-timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_pyramid.py -q -m gpu -x -k "size_specialised" > gpurun_out/san6_memcheck_special.log 2>&1; echo "memcheck exit $?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/san6_memcheck_special.log | tail -3
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_reference_2gpu.json 2> gpurun_out/bench_reference_2gpu.err; echo "reference arm under torchrun exit $?"; grep -c '^{' gpurun_out/bench_reference_2gpu.json
