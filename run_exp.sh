@@ -1,10 +1,7 @@
 #!/bin/bash
-# 2-GPU sanity of the final build: NCCL determinism test + the two multi-GPU bench lines
+# profiling round trip of the final build: launch list of one step, --set full of the specialised tail kernel
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py -q -m gpu -x > gpurun_out/test_gpu_multi_2gpu.log 2>&1; echo "multi test exit $?"; tail -2 gpurun_out/test_gpu_multi_2gpu.log
-for c in e2e videos; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config $c --steps 5 --warmup 3 > gpurun_out/bench_${c}_2gpu.json 2> gpurun_out/bench_${c}_2gpu.err; echo "bench $c 2gpu exit $?"
-  python -c "
-import json; d=json.loads([l for l in open('gpurun_out/bench_${c}_2gpu.json') if l.startswith('{')][-1]); print('$c', d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'])"
-done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_reference_2gpu.json 2> gpurun_out/bench_reference_2gpu.err; echo "reference arm under torchrun exit $?"; grep -c '^{' gpurun_out/bench_reference_2gpu.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2_final2.csv python bench.py --quick --steps 1 --warmup 0 > gpurun_out/ncu_bench.log 2>&1; echo "ncu list exit $?"; grep -c "gpu__time_duration" gpurun_out/launches_r2_final2.csv
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:phase_tail_map -s 2 -c 2 -o gpurun_out/prof_tail2 -f python bench.py --quick --steps 1 --warmup 0 > gpurun_out/ncu_tail2.log 2>&1; echo "ncu tail exit $?"
+python tools_ncu_summary.py gpurun_out/prof_tail2.ncu-rep > gpurun_out/prof_tail2_summary.txt 2>&1; tail -40 gpurun_out/prof_tail2_summary.txt
+ls -la gpurun_out/prof_tail2.ncu-rep
