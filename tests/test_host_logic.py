@@ -148,3 +148,25 @@ def test_c_abi_exports_every_declared_symbol():
     import _native
     assert sorted(_native.EXPORTED_SYMBOLS) == declared
     assert _native.lib().mimamo_abi_version() == 1
+
+
+def test_reference_arm_contract():
+    """`bench.py --impl reference`: rank 0 prints ONE JSON line with the arm's keys (the reference's own classes from
+    baseline/_ref when staged, the oracle port otherwise), every other rank exits 0 without work or output."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "windows/s" and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
