@@ -86,3 +86,33 @@ def test_clip_window_index_selects_the_sampler_windows(clips, frames, num_phase)
     x = torch.arange(clips * frames, dtype=torch.float32)[:, None, None].expand(clips * frames, 2, 2).contiguous()
     want = torch.stack([O.gather_windows(x[b * frames:(b + 1) * frames], 0, frames, num_phase) for b in range(clips)])
     assert torch.equal(x[idx], want.reshape(clips * frames, num_phase + 1, 2, 2))
+
+
+@settings(max_examples=60, deadline=None)
+@given(h=st.integers(2, 13), w=st.integers(2, 13), k=st.sampled_from([3, 5, 7]), seed=st.integers(0, 2 ** 16))
+def test_sub_lattice_tap_addressing(h, w, k, seed):
+    """The addressing scheme of the stride-2 k x k layers (conv_engine.cu, conv_forward): input pixel 2y + kh - pad lies on the
+    sub-lattice of parity (kh - pad) & 1 at index y + ((kh - pad) >> 1); indices outside a sub-lattice view read zero (TMA
+    out-of-bounds fill = the convolution's padding).  Emulated with numpy slicing against torch's strided convolution."""
+    import torch.nn.functional as F
+    pad = k // 2
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(1, 1, h, w, generator=g, dtype=torch.float64)
+    wt = torch.randn(1, 1, k, k, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, wt, stride=2, padding=pad)[0, 0].numpy()
+    ho, wo = ref.shape
+    xn = x[0, 0].numpy()
+    views = {(ph, pw): xn[ph::2, pw::2] for ph in (0, 1) for pw in (0, 1)}     # what the four tensor maps describe
+    for (ph, pw), v in views.items():
+        assert v.shape == ((h - ph + 1) // 2, (w - pw + 1) // 2)               # the extents conv_forward encodes
+    out = np.zeros((ho, wo))
+    for kh in range(k):
+        for kw in range(k):
+            oh, ow = kh - pad, kw - pad
+            v = views[(oh & 1, ow & 1)]
+            for y in range(ho):
+                for xx in range(wo):
+                    iy, ix = y + (oh >> 1), xx + (ow >> 1)                      # box coordinate of this output pixel in the view
+                    if 0 <= iy < v.shape[0] and 0 <= ix < v.shape[1]:
+                        out[y, xx] += wt[0, 0, kh, kw].item() * v[iy, ix]
+    assert np.abs(out - ref).max() < 1e-12
